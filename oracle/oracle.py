@@ -1,0 +1,114 @@
+"""ctypes wrapper around oracle/liboracle_stage1.so.
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module.  The product path
+(mojo_simdjson_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SUCCESS, CAPACITY, UTF8_ERROR, EMPTY, UNESCAPED_CHARS, UNCLOSED_STRING, UNEXPECTED_ERROR = 0, 1, 11, 13, 14, 15, 24
+FLAG_VALIDATE_UTF8 = 1
+
+
+def build(native: bool = False) -> str:
+    target = "liboracle_stage1_native.so" if native else "liboracle_stage1.so"
+    path = os.path.join(_HERE, target)
+    src = os.path.join(_HERE, "stage1_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, target])
+    return path
+
+
+_libs: dict[bool, C.CDLL] = {}
+
+
+def lib(native: bool = False) -> C.CDLL:
+    if native not in _libs:
+        L = C.CDLL(build(native))
+        u8p, u32p, u64p, i32p = C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+        for name in ("oracle_stage1_ref", "oracle_stage1_spec"):
+            f = getattr(L, name)
+            f.restype = C.c_int32
+            f.argtypes = [u8p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_uint32), u64p, i32p, C.c_uint32]
+        L.oracle_stage1_fast.restype = C.c_int32
+        L.oracle_stage1_fast.argtypes = [u8p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_uint32), u64p, C.c_uint32]
+        L.oracle_stage1_ref_trace.restype = C.c_int32
+        L.oracle_stage1_ref_trace.argtypes = [u8p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_uint32), C.c_char_p]
+        for name in ("oracle_utf8_valid_dfa", "oracle_utf8_valid_kl"):
+            f = getattr(L, name)
+            f.restype = C.c_int32
+            f.argtypes = [u8p, C.c_uint64]
+        L.oracle_index_digest.restype = None
+        L.oracle_index_digest.argtypes = [u32p, C.c_uint64, u64p, u64p]
+        L.oracle_set_shuffle_variant.restype = None
+        L.oracle_set_shuffle_variant.argtypes = [C.c_int]
+        _libs[native] = L
+    return _libs[native]
+
+
+@dataclass
+class Stage1Result:
+    error: int
+    n: int | None          # n_structural_indexes as the reference would have assigned it (None: not assigned)
+    n_written: int         # entries the indexer wrote (also on the early-return error paths)
+    indexes: np.ndarray    # uint32, n_written entries (+3 trailer entries when the trailer was written)
+    utf8_error: int        # 1 iff the input is not valid UTF-8 (always computed)
+    trailer_written: bool
+
+
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8
+        return np.ascontiguousarray(data)
+    if isinstance(data, str):
+        data = data.encode("utf-8")
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def stage1(data, flags: int = 0, impl: str = "ref", cap: int | None = None, native: bool = False) -> Stage1Result:
+    """Run the oracle.  impl: 'ref' (block restatement), 'spec' (per-byte closed form), 'fast'."""
+    L = lib(native)
+    a = _as_u8(data)
+    n_bytes = int(a.size)
+    if cap is None:
+        cap = n_bytes + 3
+    out = np.full(max(cap, 1), 0xDEADBEEF, dtype=np.uint32)
+    n = C.c_uint32(0xFFFFFFFF)
+    nw = C.c_uint64(0)
+    u8 = C.c_int32(0)
+    ptr = a.ctypes.data if n_bytes else None
+    if impl == "fast":
+        err = L.oracle_stage1_fast(ptr, n_bytes, out.ctypes.data, cap, C.byref(n), C.byref(nw), flags)
+        u8.value = 0 if L.oracle_utf8_valid_dfa(ptr, n_bytes) else 1
+    else:
+        f = L.oracle_stage1_ref if impl == "ref" else L.oracle_stage1_spec
+        err = f(ptr, n_bytes, out.ctypes.data, cap, C.byref(n), C.byref(nw), C.byref(u8), flags)
+    assigned = n.value != 0xFFFFFFFF
+    trailer = assigned
+    count = int(nw.value)
+    keep = min(count + (3 if trailer else 0), cap)
+    return Stage1Result(err, n.value if assigned else None, count, out[:keep].copy(), int(u8.value), trailer)
+
+
+def utf8_valid(data, impl: str = "dfa") -> bool:
+    L = lib()
+    a = _as_u8(data)
+    f = L.oracle_utf8_valid_dfa if impl == "dfa" else L.oracle_utf8_valid_kl
+    return bool(f(a.ctypes.data if a.size else None, int(a.size)))
+
+
+def index_digest(idx: np.ndarray) -> tuple[int, int]:
+    L = lib()
+    a = np.ascontiguousarray(idx, dtype=np.uint32)
+    d0, d1 = C.c_uint64(0), C.c_uint64(0)
+    L.oracle_index_digest(a.ctypes.data if a.size else None, int(a.size), C.byref(d0), C.byref(d1))
+    return d0.value, d1.value
