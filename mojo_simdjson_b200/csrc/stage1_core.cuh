@@ -1,0 +1,388 @@
+// stage1_core.cuh -- per-lane / per-warp arithmetic of the B200 stage-1 structural indexer.
+//
+// Everything in this header is a pure function of registers, written once and compiled twice:
+// by nvcc into the sm_100a kernel (stage1_kernel.cu) and by g++ into the host-side lane emulator
+// used by the CPU tests (tests/emu/emulate_stage1.cpp) so that every bit trick is checked against
+// the oracle without a GPU.  Nothing here touches memory.
+//
+// What it replaces in the reference (paths relative to /root/reference/src/mojo_simdjson/):
+//   eq / pack_bits byte compares            stuff.mojo:6-9
+//   classify (whitespace / op nibble tables) haswell.mojo:22-74, generic/json_character_block.mojo:22-23
+//   escape scanner                           generic/stage1/json_escape_scanner.mojo:18-45
+//   prefix_xor / in_string                   stuff.mojo:21-28, generic/stage1/json_string_scanner.mojo:55-69
+//   structural_start / follows               generic/stage1/json_scanner.mojo:24-49,64-79
+//   unescaped control characters             generic/stage1/json_structural_indexer.mojo:129-145
+//   Utf8Checker (a stub in the reference)    generic/stage1/json_structural_indexer.mojo:16-30
+//
+// Design: one lane owns 64 consecutive input bytes (16 x u32).  The bytes are transposed into eight
+// bit planes (plane k, bit i = bit k of byte i) with a 4x4 byte transpose (PRMT) followed by a
+// three-stage nibble/pair/bit butterfly; every character class is then a handful of LOP3s evaluated
+// for 32 bytes per instruction, and the class masks come out directly as the 64-bit words that the
+// escape / in-string / structural algebra needs.  No per-byte compares, no ballots for classification.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SJ_HD __host__ __device__ __forceinline__
+#else
+#define SJ_HD inline
+#endif
+
+namespace sjb200 {
+
+// ------------------------------------------------------------------------------------------------
+// portable intrinsics
+// ------------------------------------------------------------------------------------------------
+SJ_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t both = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t s = (sel >> (4 * i)) & 7;
+        r |= (uint32_t)((both >> (8 * s)) & 0xFF) << (8 * i);
+    }
+    return r;
+#endif
+}
+SJ_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SJ_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+SJ_HD int clz32(uint32_t x) {  // clz32(0) == 32
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+SJ_HD int clz64(uint64_t x) {  // clz64(0) == 64
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+SJ_HD int ffs32(uint32_t x) {  // 1-based, 0 if none
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return x ? __builtin_ctz(x) + 1 : 0;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// bytes -> bit planes (32 bytes = 8 words at a time)
+// ------------------------------------------------------------------------------------------------
+// rows a,b,c,d (4 bytes each) -> o_k = [a.k, b.k, c.k, d.k]
+SJ_HD void byte_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t &o0, uint32_t &o1, uint32_t &o2,
+                           uint32_t &o3) {
+    uint32_t t0 = prmt(a, b, 0x5140);  // a0 b0 a1 b1
+    uint32_t t1 = prmt(a, b, 0x7362);  // a2 b2 a3 b3
+    uint32_t t2 = prmt(c, d, 0x5140);  // c0 d0 c1 d1
+    uint32_t t3 = prmt(c, d, 0x7362);  // c2 d2 c3 d3
+    o0 = prmt(t0, t2, 0x5410);
+    o1 = prmt(t0, t2, 0x7632);
+    o2 = prmt(t1, t3, 0x5410);
+    o3 = prmt(t1, t3, 0x7632);
+}
+
+// exchange the bit-field selected by ~m in a with the field selected by m in b (delta swap across regs)
+SJ_HD void field_swap(uint32_t &a, uint32_t &b, uint32_t m, int s) {
+    uint32_t na = (a & m) | ((b << s) & ~m);
+    uint32_t nb = ((a >> s) & m) | (b & ~m);
+    a = na;
+    b = nb;
+}
+
+// w[0..7]: 32 consecutive bytes (little endian words).  p[k] bit i = bit k of byte i.
+SJ_HD void bitplanes32(const uint32_t w[8], uint32_t p[8]) {
+    // byte transpose so that register i, byte b holds input byte 8b+i
+    byte_transpose4(w[0], w[2], w[4], w[6], p[0], p[1], p[2], p[3]);
+    byte_transpose4(w[1], w[3], w[5], w[7], p[4], p[5], p[6], p[7]);
+    // 8x8 bit transpose inside every byte lane, across the 8 registers
+    field_swap(p[0], p[4], 0x0F0F0F0Fu, 4);
+    field_swap(p[1], p[5], 0x0F0F0F0Fu, 4);
+    field_swap(p[2], p[6], 0x0F0F0F0Fu, 4);
+    field_swap(p[3], p[7], 0x0F0F0F0Fu, 4);
+    field_swap(p[0], p[2], 0x33333333u, 2);
+    field_swap(p[1], p[3], 0x33333333u, 2);
+    field_swap(p[4], p[6], 0x33333333u, 2);
+    field_swap(p[5], p[7], 0x33333333u, 2);
+    field_swap(p[0], p[1], 0x55555555u, 1);
+    field_swap(p[2], p[3], 0x55555555u, 1);
+    field_swap(p[4], p[5], 0x55555555u, 1);
+    field_swap(p[6], p[7], 0x55555555u, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// character classes on planes (32 bytes per instruction)
+// ------------------------------------------------------------------------------------------------
+struct Classes32 {
+    uint32_t bs;   // '\\'
+    uint32_t rq;   // '"' (raw, before escape resolution)
+    uint32_t op;   // , : [ ] { } and the reference's 0x0C / 0x1A artefacts (haswell.mojo:44-69)
+    uint32_t ws;   // 0x20 0x09 0x0A 0x0D
+    uint32_t ctl;  // <= 0x1F
+};
+struct Utf8Pre32 {
+    uint32_t hi;    // >= 0x80
+    uint32_t cont;  // 10xxxxxx
+    uint32_t A;     // >= 0xC0 (any lead)
+    uint32_t B;     // >= 0xE0 (3/4-byte lead)
+    uint32_t C;     // >= 0xF0 (4-byte lead, incl. the invalid F5..FF)
+    uint32_t bad;   // C0 C1 F5..FF
+    uint32_t U;     // E0 | F0: next byte must have a minimum value
+    uint32_t V;     // ED | F4: next byte must have a maximum value
+    uint32_t W;     // F0 | F4: selects the 4-byte variant of U / V
+    uint32_t p5, p4;
+};
+
+template <bool UTF8>
+SJ_HD void classify32(const uint32_t p[8], Classes32 &c, Utf8Pre32 &u8) {
+    const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4], p5 = p[5], p6 = p[6], p7 = p[7];
+    const uint32_t u = ~p7 & ~p6;         // 00xx xxxx
+    const uint32_t v = ~p7 & p6;          // 01xx xxxx
+    const uint32_t h0 = u & ~p5 & ~p4;    // high nibble 0
+    const uint32_t h2 = u & p5 & ~p4;     // high nibble 2
+    const uint32_t h5 = v & ~p5 & p4;     // high nibble 5
+    const uint32_t k1 = u & ~p4;          // high nibble 0 or 2
+    const uint32_t k2 = u & p4;           // high nibble 1 or 3
+    const uint32_t k3 = v & p4;           // high nibble 5 or 7
+    const uint32_t a = p3 & ~p2, b = p3 & p2, cc = ~p3 & ~p2;
+    const uint32_t loA = a & p1 & ~p0, loB = a & p1 & p0, lo9 = a & ~p1 & p0;
+    const uint32_t loC = b & ~p1 & ~p0, loD = b & ~p1 & p0;
+    const uint32_t lo0 = cc & ~p1 & ~p0, lo2 = cc & p1 & ~p0;
+    c.ws = (h0 & (lo9 | loA | loD)) | (h2 & lo0);
+    c.rq = h2 & lo2;
+    c.bs = h5 & loC;
+    c.op = (k1 & loC) | (k2 & loA) | (k3 & (loB | loD));
+    c.ctl = u & ~p5;
+    if (UTF8) {
+        const uint32_t A = p7 & p6, B = A & p5, C = B & p4;
+        const uint32_t L3 = B & ~p4;
+        const uint32_t lo4 = ~p3 & p2 & ~p1 & ~p0;
+        u8.hi = p7;
+        u8.cont = p7 & ~p6;
+        u8.A = A;
+        u8.B = B;
+        u8.C = C;
+        u8.bad = (A & ~p5 & ~p4 & ~p3 & ~p2 & ~p1) | (C & (p3 | (p2 & (p1 | p0))));
+        u8.U = B & lo0;                    // E0, F0 (also F8..: already bad)
+        u8.V = (L3 & loD) | (C & lo4);     // ED, F4
+        u8.W = C & (lo0 | lo4);            // F0, F4
+        u8.p5 = p5;
+        u8.p4 = p4;
+    }
+}
+
+SJ_HD uint64_t join64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// ------------------------------------------------------------------------------------------------
+// UTF-8 (RFC 3629) in bit-sliced form.  Same error classes as the Keiser-Lemire lookup tables
+// (TOO_SHORT / TOO_LONG / TWO_CONTS = "must be continuation" xor "is continuation"; OVERLONG_2 = C0,C1;
+// OVERLONG_3 = E0 + 80..9F; SURROGATE = ED + A0..BF; OVERLONG_4 = F0 + 80..8F; TOO_LARGE = F4 + 90..BF,
+// F5..FF), evaluated on the planes the classifier already has instead of three nibble lookups per byte.
+// ------------------------------------------------------------------------------------------------
+struct Utf8Carry {       // what the three bytes before this lane's chunk demand of its first bytes
+    uint32_t must;       // bit j: byte j of the chunk must be a continuation (j = 0..2)
+    uint32_t u, v, w;    // bit 0: byte -1 was E0|F0 / ED|F4 / F0|F4
+};
+
+// prev = the 4 bytes preceding the chunk, little endian (byte -1 is the top byte)
+SJ_HD Utf8Carry utf8_carry_from_prev_word(uint32_t prev) {
+    Utf8Carry c;
+    const uint32_t x1 = prev >> 24, x2 = (prev >> 16) & 0xFF, x3 = (prev >> 8) & 0xFF;
+    uint32_t k = 0;                       // number of leading bytes of the chunk that must continue
+    if (x3 >= 0xF0) k = 1;
+    if (x2 >= 0xE0) k = 1;
+    if (x2 >= 0xF0) k = 2;
+    if (x1 >= 0xC0) k = k > 1 ? k : 1;
+    if (x1 >= 0xE0) k = 2;
+    if (x1 >= 0xF0) k = 3;
+    c.must = (1u << k) - 1u;
+    c.u = (x1 == 0xE0) | (x1 == 0xF0);
+    c.v = (x1 == 0xED) | (x1 == 0xF4);
+    c.w = (x1 == 0xF0) | (x1 == 0xF4);
+    // F5..FF / C0 C1 in the previous bytes were already reported by the lane that owns them
+    return c;
+}
+
+// returns non-zero iff this chunk (given what precedes it) violates UTF-8; *tail_must = number of
+// continuation bytes still owed after the last byte of the chunk (for the end-of-input check)
+SJ_HD uint64_t utf8_errors64(const Utf8Pre32 &l, const Utf8Pre32 &h, const Utf8Carry &cin, uint32_t *tail_must) {
+    const uint64_t A = join64(l.A, h.A), B = join64(l.B, h.B), C = join64(l.C, h.C);
+    const uint64_t cont = join64(l.cont, h.cont), bad = join64(l.bad, h.bad);
+    const uint64_t U = join64(l.U, h.U), V = join64(l.V, h.V), W = join64(l.W, h.W);
+    const uint64_t p5 = join64(l.p5, h.p5), p4 = join64(l.p4, h.p4);
+    const uint64_t must = (A << 1) | (B << 2) | (C << 3) | cin.must;
+    const uint64_t Us = (U << 1) | cin.u, Vs = (V << 1) | cin.v, Ws = (W << 1) | cin.w;
+    const uint64_t w4 = Ws & p4;
+    const uint64_t err = (must ^ cont) | bad | (Us & ~p5 & ~w4) | (Vs & (p5 | w4));
+    *tail_must = (uint32_t)((A >> 63) | (B >> 62) | (C >> 61));
+    return err;
+}
+
+// ------------------------------------------------------------------------------------------------
+// escapes, quotes, strings
+// ------------------------------------------------------------------------------------------------
+// Positions escaped by a backslash, given that the chunk's first byte is (e_in=1) or is not escaped
+// by the previous chunk.  Add-carry formulation of upstream simdjson's escape scanner as used by the
+// reference (json_escape_scanner.mojo:18-45): within a run of backslashes the ones at even distance
+// from the run start are escapes, the bytes right after them are escaped.
+SJ_HD uint64_t escaped_mask(uint64_t bs, uint64_t e_in) {
+    const uint64_t ODD = 0xAAAAAAAAAAAAAAAAull;
+    const uint64_t potential = bs & ~e_in;
+    const uint64_t code = (((potential << 1) | ODD) - potential) ^ ODD;
+    return code ^ (bs | e_in);
+}
+
+SJ_HD uint64_t prefix_xor64(uint64_t x) {
+    x ^= x << 1;
+    x ^= x << 2;
+    x ^= x << 4;
+    x ^= x << 8;
+    x ^= x << 16;
+    x ^= x << 32;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Carry algebra.  The state entering a span of bytes is (e, s, p):
+//   e = its first byte is escaped, s = it starts inside a string, p = the byte before it is a
+//   non-quote scalar.  What a span does to that state depends on e only (never on s or p), so a span
+//   is summarised, for e = 0 and e = 1 separately, by (e_out, s_flip, p_out): 6 bits + an identity flag.
+//   bit 0/3: e_out   bit 1/4: s_flip   bit 2/5: p_out   (for e_in = 0 / 1);   bit 6: identity
+// Composition is associative; it is used across the warps of a tile and across tiles (decoupled
+// look-back).  Replaces the three sequential 1-bit carries of the reference.
+// ------------------------------------------------------------------------------------------------
+typedef uint32_t SpanFn;
+static const SpanFn SPAN_IDENT = 1u << 6;
+
+SJ_HD SpanFn span_make(uint32_t eo0, uint32_t fl0, uint32_t po0, uint32_t eo1, uint32_t fl1, uint32_t po1) {
+    return (eo0 & 1) | ((fl0 & 1) << 1) | ((po0 & 1) << 2) | ((eo1 & 1) << 3) | ((fl1 & 1) << 4) | ((po1 & 1) << 5);
+}
+// constant function: whatever comes in, the state after is (e, s, p) -- s relative to "outside a string"
+SJ_HD SpanFn span_const(uint32_t e, uint32_t s, uint32_t p) { return span_make(e, s, p, e, s, p); }
+
+SJ_HD SpanFn span_compose(SpanFn older, SpanFn newer) {  // apply older first, then newer
+    if (older & SPAN_IDENT) return newer;
+    if (newer & SPAN_IDENT) return older;
+    SpanFn r = 0;
+    for (int e = 0; e < 2; e++) {
+        const uint32_t a = (older >> (3 * e)) & 7;
+        const uint32_t b = (newer >> (3 * (a & 1))) & 7;
+        const uint32_t o = (b & 1) | ((a ^ b) & 2) | (b & 4);
+        r |= o << (3 * e);
+    }
+    return r;
+}
+
+struct CarryState {
+    uint32_t e, s, p;
+};
+SJ_HD CarryState span_apply(SpanFn f, CarryState in) {
+    if (f & SPAN_IDENT) return in;
+    const uint32_t a = (f >> (3 * (in.e & 1))) & 7;
+    CarryState o;
+    o.e = a & 1;
+    o.s = in.s ^ ((a >> 1) & 1);
+    o.p = (a >> 2) & 1;
+    return o;
+}
+SJ_HD uint32_t carry_pack(CarryState c) { return (c.e & 1) | ((c.s & 1) << 1) | ((c.p & 1) << 2); }
+SJ_HD CarryState carry_unpack(uint32_t v) {
+    CarryState c;
+    c.e = v & 1;
+    c.s = (v >> 1) & 1;
+    c.p = (v >> 2) & 1;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-level escape summary and in-warp resolution from two ballots
+//   A = ballot(lane is all backslashes), O = ballot(parity of the lane's trailing backslash run)
+// ------------------------------------------------------------------------------------------------
+SJ_HD bool lane_all_backslash(uint64_t bs) { return bs == ~0ull; }
+SJ_HD uint32_t lane_trailing_run_parity(uint64_t bs) { return (uint32_t)clz64(~bs) & 1u; }
+
+// e_in of `lane` (0..32; 32 = the carry leaving the warp) assuming the warp's own e_in is 0.
+// *lead = every earlier lane of the warp is all backslashes, i.e. the warp's e_in passes straight through.
+SJ_HD uint32_t warp_lane_e_in(uint32_t A, uint32_t O, int lane, bool *lead) {
+    const uint32_t below = ~A & (lane >= 32 ? 0xFFFFFFFFu : ((1u << lane) - 1u));
+    *lead = (below == 0);
+    if (below == 0) return 0;
+    const int j = 31 - clz32(below);
+    return (O >> j) & 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Everything a lane keeps between the phases of a tile
+// ------------------------------------------------------------------------------------------------
+struct LaneMasks {
+    uint64_t bs, rq, op, ws, ctl;
+    uint64_t quote;   // unescaped quotes (under the e_in assumed so far)
+    uint64_t ps;      // prefix xor of quote (in_string relative to the chunk start)
+    uint64_t flipq;   // the one raw quote whose escapedness flips if the warp's e_in turns out to be 1
+};
+
+// phase 1b: after the lane knows its e_in (assuming warp e_in = 0)
+SJ_HD void lane_resolve_quotes(LaneMasks &m, uint32_t e_in, bool lead) {
+    const uint64_t esc = escaped_mask(m.bs, (uint64_t)e_in);
+    m.quote = m.rq & ~esc;
+    m.ps = prefix_xor64(m.quote);
+    // first non-backslash byte of a leading lane: its escapedness is the warp carry xor run parity
+    m.flipq = (lead && m.bs != ~0ull) ? (m.rq & ~m.bs & (m.bs + 1)) : 0;
+}
+// applied only when the warp's e_in is really 1
+SJ_HD void lane_apply_escape_carry(LaneMasks &m) {
+    m.quote ^= m.flipq;
+    m.ps ^= (0 - m.flipq);  // flips every position >= the quote
+}
+
+SJ_HD uint64_t lane_nonquote_scalar(const LaneMasks &m) { return ~(m.op | m.ws) & ~m.quote; }
+
+struct LaneOut {
+    uint64_t structural;
+    uint32_t unescaped_err;
+};
+// phase 2: s_in = the chunk starts inside a string, p_in = previous byte is a non-quote scalar
+SJ_HD LaneOut lane_structurals(const LaneMasks &m, uint32_t s_in, uint32_t p_in) {
+    const uint64_t in_string = m.ps ^ (0 - (uint64_t)(s_in & 1));
+    const uint64_t scalar = ~(m.op | m.ws);
+    const uint64_t nqs = scalar & ~m.quote;
+    const uint64_t follows = (nqs << 1) | (p_in & 1);
+    const uint64_t string_tail = in_string ^ m.quote;
+    LaneOut o;
+    o.structural = (m.op | (scalar & ~follows)) & ~string_tail;
+    o.unescaped_err = (m.ctl & in_string) != 0;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp summary from ballots (all under "warp e_in = 0"):
+//   A, O as above; PB = ballot(lane quote parity); NQ = ballot(bit 63 of non-quote scalar);
+//   FQ = ballot(flipq != 0); FQ63 = ballot(bit 63 of flipq)
+// ------------------------------------------------------------------------------------------------
+SJ_HD SpanFn warp_span(uint32_t A, uint32_t O, uint32_t PB, uint32_t NQ, uint32_t FQ, uint32_t FQ63) {
+    bool lead;
+    const uint32_t e_tail = warp_lane_e_in(A, O, 32, &lead);  // lead == whole warp is backslashes
+    const uint32_t pw = (uint32_t)popc32(PB) & 1u;
+    const uint32_t fw = FQ != 0;
+    const uint32_t po0 = NQ >> 31;
+    const uint32_t po1 = po0 ^ (FQ63 >> 31);
+    return span_make(lead ? 0 : e_tail, pw, po0, lead ? 1 : e_tail, pw ^ fw, po1);
+}
+
+}  // namespace sjb200
