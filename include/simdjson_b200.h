@@ -1,0 +1,154 @@
+/*
+ * simdjson_b200.h -- C ABI of libsimdjson_b200.so: the B200 (sm_100a) stage-1 structural indexer that sits
+ * behind mojo-simdjson's stage-1 API ("input buffer in -> uint32 structural index array + error code out").
+ *
+ * Flat C only (pointers and fixed-width integers; no structs by value, no callbacks, no exceptions) so that
+ * Mojo's sys.ffi.DLHandle.get_function / external_call, Python ctypes or any other FFI can bind it.
+ * Every function returns a simdjson error code (reference src/mojo_simdjson/errors.mojo:2-34) as int32_t.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference's src/mojo_simdjson/):
+ *   sjb200_stage1            -> DomParserImplementation.stage1(Span[UInt8])
+ *                               include/generic/dom_parser_implementation.mojo:65-69, i.e. the call
+ *                               JsonStructuralIndexer.index[128](buffer, self) at :69
+ *                               (generic/stage1/json_structural_indexer.mojo:81-186)
+ *   sjb200_ctx_create        -> DomParserImplementation.__init__ + allocate()
+ *                               include/generic/dom_parser_implementation.mojo:29-39, 85-89
+ *   output contract          -> structural_indexes[0..n) ascending byte offsets, [n] = [n+1] = len, [n+2] = 0,
+ *                               n_structural_indexes = n, next_structural_index = 0
+ *                               (json_structural_indexer.mojo:160-174; consumed by
+ *                               generic/stage2/json_iterator.mojo:28-38,256-288)
+ *   sjb200_batch_*           -> no reference counterpart (the reference has no NDJSON / multi-document mode,
+ *                               generic/stage2/tape_builder.mojo:25 "TODO: add streaming"); parity is defined
+ *                               as "the reference called once per line-aligned segment"
+ *
+ * Differences from the reference that a caller must know:
+ *   - the index array needs capacity >= n + 3 entries; the reference sizes it to len entries and writes the
+ *     trailer out of bounds whenever n + 3 > len (dom_parser_implementation.mojo:85-89 vs
+ *     json_structural_indexer.mojo:167-173).  Too small -> SJB200_CAPACITY instead of a wild write.
+ *   - the reference's Utf8Checker is a stub (json_structural_indexer.mojo:16-30), so it never returns
+ *     UTF8_ERROR.  Here the UTF-8 verdict is always computed and reported separately; it is folded into the
+ *     return code only when SJB200_FLAG_VALIDATE_UTF8 is set (default off = reference-exact verdicts).
+ *   - on UNCLOSED_STRING / UNESCAPED_CHARS the reference returns before assigning n_structural_indexes
+ *     (:151-158); *n_out is likewise left untouched (the indexes written so far are still delivered).
+ */
+#ifndef SIMDJSON_B200_H
+#define SIMDJSON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SJB200_ABI_VERSION 1
+
+/* error codes (subset of reference errors.mojo that stage 1 can return) */
+#define SJB200_SUCCESS 0
+#define SJB200_CAPACITY 1
+#define SJB200_MEMALLOC 2
+#define SJB200_UTF8_ERROR 11
+#define SJB200_UNINITIALIZED 12
+#define SJB200_EMPTY 13
+#define SJB200_UNESCAPED_CHARS 14
+#define SJB200_UNCLOSED_STRING 15
+#define SJB200_UNEXPECTED_ERROR 24
+
+/* flags */
+#define SJB200_FLAG_VALIDATE_UTF8 1u /* return UTF8_ERROR (lowest priority) when the input is not valid UTF-8 */
+#define SJB200_FLAG_NO_UTF8 4u       /* do not even compute the UTF-8 verdict (utf8_err_out = -1) */
+#define SJB200_FLAG_TIMING 8u        /* record CUDA events around the kernel (sjb200_last_elapsed_ms) */
+
+typedef struct sjb200_ctx sjb200_ctx;
+
+/* ABI version of the loaded library. */
+int32_t sjb200_version(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int32_t sjb200_device_count(void);
+
+/*
+ * Creates a parser context on `device`: a stream, look-back descriptors and a mapped result slot sized for
+ * documents up to max_len bytes (< 2^32), and -- unless max_len_host == 0 -- device input/output buffers for the
+ * host-to-host entry point (input max_len_host bytes, output max_len_host + 3 entries).
+ * MEMALLOC on allocation failure, CAPACITY if max_len >= 2^32, UNEXPECTED_ERROR on any other CUDA error.
+ */
+int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_host, uint32_t flags, sjb200_ctx **ctx);
+int32_t sjb200_ctx_destroy(sjb200_ctx *ctx);
+
+/* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
+int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
+/* Force the tile shape: warps per tile in {2,4,8}, 0 = choose from the document size. */
+int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
+
+/*
+ * Host-to-host drop-in for DomParserImplementation.stage1: copies buf to the device, indexes it, copies the
+ * n + 3 entries into idx_out.  Synchronous.  idx_capacity is in entries.
+ *   len == 0 -> EMPTY; len >= 2^32 or len > max_len_host -> CAPACITY; n + 3 > idx_capacity -> CAPACITY.
+ * utf8_err_out (may be NULL): 1 iff the input is not valid UTF-8, -1 if not computed.
+ */
+int32_t sjb200_stage1(sjb200_ctx *ctx, const uint8_t *buf, uint64_t len, uint32_t *idx_out, uint64_t idx_capacity,
+                      uint32_t *n_out, int32_t *utf8_err_out, uint32_t flags);
+
+/*
+ * Device-resident variant (what the roofline metric times): d_buf and d_idx are device pointers, any alignment
+ * for d_buf, 4-byte alignment for d_idx.  _async only enqueues on the context's stream; _finish waits and returns
+ * the verdict of the most recent _async call.  sjb200_stage1_device = _async + _finish.
+ */
+int32_t sjb200_stage1_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx,
+                                   uint64_t idx_capacity, uint32_t flags);
+int32_t sjb200_stage1_finish(sjb200_ctx *ctx, uint32_t *n_out, uint32_t *n_written_out, int32_t *utf8_err_out);
+int32_t sjb200_stage1_device(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx,
+                             uint64_t idx_capacity, uint32_t *n_out, int32_t *utf8_err_out, uint32_t flags);
+
+/* Waits for everything enqueued on the context's stream. */
+int32_t sjb200_sync(sjb200_ctx *ctx);
+
+/* Kernel-only device time (ms) of the last call made with SJB200_FLAG_TIMING; negative if none. */
+float sjb200_last_elapsed_ms(sjb200_ctx *ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t sjb200_launch_count(sjb200_ctx *ctx);
+
+/* Pinned host memory for callers that want full-speed DMA; device memory helpers for FFI callers without CUDA. */
+int32_t sjb200_pinned_alloc(uint64_t bytes, void **p);
+int32_t sjb200_pinned_free(void *p);
+int32_t sjb200_device_alloc(sjb200_ctx *ctx, uint64_t bytes, void **p);
+int32_t sjb200_device_free(sjb200_ctx *ctx, void *p);
+int32_t sjb200_copy_to_device(sjb200_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
+int32_t sjb200_copy_to_host(sjb200_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
+
+/*
+ * NDJSON / multi-document batches.  A batch is cut at '\n' into segments of at most seg_bytes (< 2^32) bytes;
+ * every segment is an independent stage-1 call with segment-relative indexes, its own trailer and verdict --
+ * exactly what the reference would produce if called once per segment.
+ *
+ * sjb200_batch_split_device: finds the cut points of a device-resident batch.  seg_offsets must hold
+ * max_segments + 1 entries; on return seg_offsets[0..*n_segments] are byte offsets (last one == len).
+ * A line longer than seg_bytes -> CAPACITY.
+ */
+int32_t sjb200_batch_split_device(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, uint64_t seg_bytes,
+                                  uint64_t *seg_offsets, uint32_t max_segments, uint32_t *n_segments);
+int32_t sjb200_batch_split_host(const uint8_t *buf, uint64_t len, uint64_t seg_bytes, uint64_t *seg_offsets,
+                                uint32_t max_segments, uint32_t *n_segments);
+/*
+ * Indexes segments [first, first+count) of a device-resident batch back to back on this context's stream.
+ * Segment s writes its indexes (+ trailer) at d_idx + idx_offsets[s] (entries; caller-chosen, typically
+ * seg_offsets[s] - seg_offsets[first] + 3 * (s - first)); seg_counts[s] / seg_errors[s] / seg_utf8[s] receive n,
+ * the verdict and the UTF-8 verdict.  Returns the worst (numerically largest) per-segment error.
+ */
+int32_t sjb200_batch_run_device(sjb200_ctx *ctx, const uint8_t *d_buf, const uint64_t *seg_offsets, uint32_t first,
+                                uint32_t count, uint32_t *d_idx, const uint64_t *idx_offsets, uint64_t idx_capacity,
+                                uint32_t *seg_counts, int32_t *seg_errors, int32_t *seg_utf8, uint32_t flags);
+
+/*
+ * Same, without waiting: only enqueues.  If d_status is not NULL, segment first+i also leaves {error, n} as two
+ * int32 at d_status[2*i] in device memory, so that the verdict exchange between GPUs (NCCL all-reduce of error
+ * flags, all-gather of counts) can be enqueued behind it with no host round trip.  Returns the worst launch error.
+ */
+int32_t sjb200_batch_run_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, const uint64_t *seg_offsets,
+                                      uint32_t first, uint32_t count, uint32_t *d_idx, const uint64_t *idx_offsets,
+                                      uint64_t idx_capacity, int32_t *d_status, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMDJSON_B200_H */

@@ -1,0 +1,462 @@
+// capi.cu -- C ABI (include/simdjson_b200.h) over the sm_100a stage-1 kernel: context, buffers, launches.
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/simdjson_b200.h"
+#include "stage1_kernel.cuh"
+
+using namespace sjb200;
+
+namespace {
+
+constexpr uint32_t RESULT_SLOTS = 256;
+constexpr uint64_t MIN_TILE = 2 * 2048;
+
+inline int32_t cuda_err(cudaError_t e) {
+    if (e == cudaSuccess) return SJB200_SUCCESS;
+    if (e == cudaErrorMemoryAllocation) return SJB200_MEMALLOC;
+    fprintf(stderr, "[simdjson_b200] CUDA error: %s\n", cudaGetErrorString(e));
+    return SJB200_UNEXPECTED_ERROR;
+}
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e__ = (call);                 \
+        if (e__ != cudaSuccess) return cuda_err(e__); \
+    } while (0)
+
+}  // namespace
+
+struct sjb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t max_len = 0, max_len_host = 0;
+    uint8_t *d_in = nullptr;        // host-path input staging on the device
+    uint32_t *d_out = nullptr;      // host-path output on the device
+    uint64_t d_out_cap = 0;
+    uint64_t *desc1 = nullptr, *desc2 = nullptr;
+    uint32_t max_tiles = 0;
+    uint32_t *ticket = nullptr;
+    Stage1Result *h_results = nullptr;  // mapped pinned, RESULT_SLOTS entries
+    Stage1Result *d_results = nullptr;  // device alias of h_results
+    uint32_t slot = 0;                  // slot used by the most recent launch
+    uint32_t gen = 0;
+    int forced_warps = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    uint32_t last_flags = 0;
+    bool pending = false;
+    uint64_t *d_split = nullptr;        // scratch for batch_split_device
+};
+
+namespace {
+
+template <int WARPS, bool UTF8>
+cudaError_t launch_cfg(const Stage1Params &p, cudaStream_t s) {
+    using Cfg = TileCfg<WARPS>;
+    stage1_kernel<WARPS, UTF8><<<p.ntiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+
+int pick_warps(const sjb200_ctx *c, uint64_t alen) {
+    if (c->forced_warps) return c->forced_warps;
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("SJB200_WARPS");
+        env = e ? atoi(e) : 0;
+        if (env != 2 && env != 4 && env != 8) env = 0;
+    }
+    if (env) return env;
+    // small documents: smaller tiles so that the work spreads over all 148 SMs
+    if (alen >= (uint64_t)148 * 4 * 16384) return 8;
+    if (alen >= (uint64_t)148 * 4 * 8192) return 4;
+    return 2;
+}
+
+// enqueue one stage-1 kernel; the result lands in result slot `slot`
+int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap, uint32_t flags,
+                uint32_t slot, int32_t *d_status = nullptr) {
+    Stage1Params p;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
+    p.mis = (uint32_t)(addr & 15u);
+    p.abase = d_buf - p.mis;
+    p.alen = (uint64_t)p.mis + len;
+    p.len = (uint32_t)len;
+    p.out = d_idx;
+    p.cap = cap;
+    p.desc1 = c->desc1;
+    p.desc2 = c->desc2;
+    p.ticket = c->ticket;
+    p.result = c->d_results + slot;
+    p.dev_status = d_status;
+    c->gen++;
+    if ((c->gen & 0x0FFFFFFFu) == 0) c->gen++;  // generation 0 is the cleared state of the descriptors
+    p.gen = c->gen;
+    p.flags = flags;
+    const int warps = pick_warps(c, p.alen);
+    const uint64_t tile = (uint64_t)warps * 2048;
+    const uint64_t ntiles = (p.alen + tile - 1) / tile;
+    if (ntiles > c->max_tiles) return SJB200_CAPACITY;
+    p.ntiles = (uint32_t)ntiles;
+    const bool utf8 = !(flags & SJB200_FLAG_NO_UTF8);
+    cudaError_t e;
+    if (c->timed) cudaEventRecord(c->ev0, c->stream);
+    switch (warps) {
+    case 8: e = utf8 ? launch_cfg<8, true>(p, c->stream) : launch_cfg<8, false>(p, c->stream); break;
+    case 4: e = utf8 ? launch_cfg<4, true>(p, c->stream) : launch_cfg<4, false>(p, c->stream); break;
+    default: e = utf8 ? launch_cfg<2, true>(p, c->stream) : launch_cfg<2, false>(p, c->stream); break;
+    }
+    if (c->timed) cudaEventRecord(c->ev1, c->stream);
+    c->launches++;
+    return cuda_err(e);
+}
+
+int32_t check_args(sjb200_ctx *c, uint64_t len, uint32_t flags) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (len == 0) return SJB200_EMPTY;                 // json_structural_indexer.mojo:91-92
+    if (len > 0xFFFFFFFFull || len > c->max_len) return SJB200_CAPACITY;  // :87-89, base.mojo:2
+    c->timed = (flags & SJB200_FLAG_TIMING) != 0;
+    return SJB200_SUCCESS;
+}
+
+__global__ void split_kernel(const uint8_t *buf, uint64_t len, uint64_t seg_bytes, uint64_t *cuts, uint32_t ncuts) {
+    // one warp per cut k: the position after the last '\n' inside (k*seg_bytes, min((k+1)*seg_bytes, len)],
+    // or len itself for the final cut; ~0 if that window holds no newline.
+    const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= ncuts) return;
+    const uint64_t hi = (uint64_t)(k + 1) * seg_bytes;
+    if (hi >= len) {
+        if (lane == 0) cuts[k] = len;
+        return;
+    }
+    const uint64_t lo = (uint64_t)k * seg_bytes;
+    uint64_t found = ~0ull;
+    for (uint64_t end = hi; end > lo;) {
+        const uint64_t span = end - lo < 32 ? end - lo : 32;
+        const bool hit = (uint64_t)lane < span && buf[end - 1 - lane] == '\n';
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, hit);
+        if (b) {
+            found = end - (uint64_t)(__ffs((int)b) - 1);  // the byte after the newline
+            break;
+        }
+        end -= span;
+    }
+    if (lane == 0) cuts[k] = found;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sjb200_version(void) { return SJB200_ABI_VERSION; }
+
+int32_t sjb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_host, uint32_t flags, sjb200_ctx **out) {
+    (void)flags;
+    if (!out) return SJB200_UNINITIALIZED;
+    *out = nullptr;
+    if (max_len > 0xFFFFFFFFull || max_len_host > max_len) return SJB200_CAPACITY;
+    CK(cudaSetDevice(device));
+    sjb200_ctx *c = new (std::nothrow) sjb200_ctx();
+    if (!c) return SJB200_MEMALLOC;
+    c->device = device;
+    c->max_len = max_len;
+    c->max_len_host = max_len_host;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    c->own_stream = (e == cudaSuccess);
+    c->max_tiles = (uint32_t)((max_len + 16 + MIN_TILE - 1) / MIN_TILE + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&c->desc1, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->desc2, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ticket, 256);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_split, 8 * 4096);
+    if (e == cudaSuccess) e = cudaMemset(c->desc1, 0, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMemset(c->desc2, 0, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMemset(c->ticket, 0, 256);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_results, sizeof(Stage1Result) * RESULT_SLOTS, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->d_results, c->h_results, 0);
+    if (e == cudaSuccess && max_len_host) {
+        e = cudaMalloc(&c->d_in, (size_t)max_len_host + 256);
+        c->d_out_cap = max_len_host + 3;
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_out, (size_t)(c->d_out_cap + 4) * 4);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) {
+        // the staged tile needs no opt-in (< 48 KiB) but ask for the shared-memory carveout we want
+        cudaFuncSetAttribute(stage1_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(stage1_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+        const int32_t code = cuda_err(e);
+        sjb200_ctx_destroy(c);
+        return code;
+    }
+    memset(c->h_results, 0, sizeof(Stage1Result) * RESULT_SLOTS);
+    *out = c;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
+    if (!c) return SJB200_SUCCESS;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    cudaFree(c->desc1);
+    cudaFree(c->desc2);
+    cudaFree(c->ticket);
+    cudaFree(c->d_split);
+    if (c->h_results) cudaFreeHost(c->h_results);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_set_stream(sjb200_ctx *c, void *cuda_stream) {
+    if (!c) return SJB200_UNINITIALIZED;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_set_warps(sjb200_ctx *c, int32_t warps) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (warps != 0 && warps != 2 && warps != 4 && warps != 8) return SJB200_UNEXPECTED_ERROR;
+    c->forced_warps = warps;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_stage1_device_async(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx,
+                                   uint64_t idx_capacity, uint32_t flags) {
+    int32_t rc = check_args(c, len, flags);
+    if (rc != SJB200_SUCCESS) {
+        if (c) c->pending = false;
+        return rc;
+    }
+    CK(cudaSetDevice(c->device));
+    c->slot = (c->slot + 1) % RESULT_SLOTS;
+    c->last_flags = flags;
+    rc = enqueue(c, d_buf, len, d_idx, idx_capacity, flags, c->slot);
+    c->pending = (rc == SJB200_SUCCESS);
+    return rc;
+}
+
+int32_t sjb200_stage1_finish(sjb200_ctx *c, uint32_t *n_out, uint32_t *n_written_out, int32_t *utf8_err_out) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (!c->pending) return SJB200_UNINITIALIZED;
+    CK(cudaStreamSynchronize(c->stream));
+    c->pending = false;
+    const Stage1Result r = c->h_results[c->slot];
+    if (r.n_valid && n_out) *n_out = r.n;  // untouched on the reference's early-return paths
+    if (n_written_out) *n_written_out = r.n_written;
+    if (utf8_err_out) *utf8_err_out = (c->last_flags & SJB200_FLAG_NO_UTF8) ? -1 : r.utf8_error;
+    return r.error;
+}
+
+int32_t sjb200_stage1_device(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t idx_capacity,
+                             uint32_t *n_out, int32_t *utf8_err_out, uint32_t flags) {
+    const int32_t rc = sjb200_stage1_device_async(c, d_buf, len, d_idx, idx_capacity, flags);
+    if (rc != SJB200_SUCCESS) return rc;
+    return sjb200_stage1_finish(c, n_out, nullptr, utf8_err_out);
+}
+
+int32_t sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, uint64_t len, uint32_t *idx_out, uint64_t idx_capacity,
+                      uint32_t *n_out, int32_t *utf8_err_out, uint32_t flags) {
+    int32_t rc = check_args(c, len, flags);
+    if (rc != SJB200_SUCCESS) return rc;
+    if (len > c->max_len_host || !c->d_in) return SJB200_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d_in, buf, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t cap = idx_capacity < c->d_out_cap ? idx_capacity : c->d_out_cap;
+    c->slot = (c->slot + 1) % RESULT_SLOTS;
+    c->last_flags = flags;
+    rc = enqueue(c, c->d_in, len, c->d_out, cap, flags, c->slot);
+    if (rc != SJB200_SUCCESS) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    const Stage1Result r = c->h_results[c->slot];
+    uint64_t ncopy = r.n_written < cap ? r.n_written : cap;
+    if (r.n_valid) ncopy = (uint64_t)r.n + 3;  // trailer included
+    if (ncopy) {
+        CK(cudaMemcpyAsync(idx_out, c->d_out, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (r.n_valid && n_out) *n_out = r.n;
+    if (utf8_err_out) *utf8_err_out = (flags & SJB200_FLAG_NO_UTF8) ? -1 : r.utf8_error;
+    return r.error;
+}
+
+int32_t sjb200_sync(sjb200_ctx *c) {
+    if (!c) return SJB200_UNINITIALIZED;
+    CK(cudaStreamSynchronize(c->stream));
+    return SJB200_SUCCESS;
+}
+
+float sjb200_last_elapsed_ms(sjb200_ctx *c) {
+    if (!c || !c->timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+uint64_t sjb200_launch_count(sjb200_ctx *c) { return c ? c->launches : 0; }
+
+int32_t sjb200_pinned_alloc(uint64_t bytes, void **p) {
+    if (!p) return SJB200_UNINITIALIZED;
+    CK(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
+    return SJB200_SUCCESS;
+}
+int32_t sjb200_pinned_free(void *p) {
+    CK(cudaFreeHost(p));
+    return SJB200_SUCCESS;
+}
+int32_t sjb200_device_alloc(sjb200_ctx *c, uint64_t bytes, void **p) {
+    if (!c || !p) return SJB200_UNINITIALIZED;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMalloc(p, (size_t)bytes));
+    return SJB200_SUCCESS;
+}
+int32_t sjb200_device_free(sjb200_ctx *c, void *p) {
+    if (!c) return SJB200_UNINITIALIZED;
+    CK(cudaSetDevice(c->device));
+    CK(cudaFree(p));
+    return SJB200_SUCCESS;
+}
+int32_t sjb200_copy_to_device(sjb200_ctx *c, void *d_dst, const void *h_src, uint64_t bytes) {
+    if (!c) return SJB200_UNINITIALIZED;
+    CK(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SJB200_SUCCESS;
+}
+int32_t sjb200_copy_to_host(sjb200_ctx *c, void *h_dst, const void *d_src, uint64_t bytes) {
+    if (!c) return SJB200_UNINITIALIZED;
+    CK(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_batch_split_host(const uint8_t *buf, uint64_t len, uint64_t seg_bytes, uint64_t *seg_offsets,
+                                uint32_t max_segments, uint32_t *n_segments) {
+    // same rule as split_kernel: nominal cuts at multiples of seg_bytes, each moved left to a line start
+    if (!seg_offsets || !n_segments || seg_bytes == 0 || seg_bytes > 0x7FFFFFFFull) return SJB200_CAPACITY;
+    const uint64_t ncuts = (len + seg_bytes - 1) / seg_bytes;
+    if (ncuts > max_segments) return SJB200_CAPACITY;
+    uint32_t n = 0;
+    seg_offsets[0] = 0;
+    for (uint64_t k = 0; k < ncuts; k++) {
+        const uint64_t hi = (k + 1) * seg_bytes, lo = k * seg_bytes;
+        uint64_t cut;
+        if (hi >= len) {
+            cut = len;
+        } else {
+            uint64_t p = hi;
+            while (p > lo && buf[p - 1] != '\n') p--;
+            if (p == lo) return SJB200_CAPACITY;  // no newline inside a whole nominal segment
+            cut = p;
+        }
+        if (cut > seg_offsets[n]) seg_offsets[++n] = cut;
+    }
+    *n_segments = n;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_batch_split_device(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint64_t seg_bytes,
+                                  uint64_t *seg_offsets, uint32_t max_segments, uint32_t *n_segments) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (!seg_offsets || !n_segments || seg_bytes == 0 || seg_bytes > 0x7FFFFFFFull) return SJB200_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    // nominal boundaries at multiples of seg_bytes, each moved left to the nearest line start
+    const uint64_t ncuts64 = (len + seg_bytes - 1) / seg_bytes;
+    if (ncuts64 > max_segments || ncuts64 > 4096) return SJB200_CAPACITY;
+    const uint32_t ncuts = (uint32_t)ncuts64;
+    if (ncuts == 0) {
+        seg_offsets[0] = 0;
+        *n_segments = 0;
+        return SJB200_SUCCESS;
+    }
+    split_kernel<<<(ncuts + 3) / 4, 128, 0, c->stream>>>(d_buf, len, seg_bytes, c->d_split, ncuts);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(seg_offsets + 1, c->d_split, (size_t)ncuts * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    seg_offsets[0] = 0;
+    uint32_t n = 0;
+    for (uint32_t k = 1; k <= ncuts; k++) {
+        if (seg_offsets[k] == ~0ull) return SJB200_CAPACITY;  // no newline inside a whole nominal segment
+        if (seg_offsets[k] > seg_offsets[n]) seg_offsets[++n] = seg_offsets[k];
+    }
+    *n_segments = n;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_batch_run_device_async(sjb200_ctx *c, const uint8_t *d_buf, const uint64_t *seg_offsets, uint32_t first,
+                                      uint32_t count, uint32_t *d_idx, const uint64_t *idx_offsets, uint64_t idx_capacity,
+                                      int32_t *d_status, uint32_t flags) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (count > RESULT_SLOTS) return SJB200_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    c->timed = false;
+    int32_t worst = SJB200_SUCCESS;
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t s = first + i;
+        const uint64_t beg = seg_offsets[s], end = seg_offsets[s + 1], len = end - beg;
+        int32_t rc;
+        const uint64_t next = (i + 1 < count) ? idx_offsets[s + 1] : idx_capacity;
+        if (len == 0) rc = SJB200_EMPTY;
+        else if (len > 0xFFFFFFFFull || len > c->max_len || next <= idx_offsets[s] || next > idx_capacity) rc = SJB200_CAPACITY;
+        else rc = enqueue(c, d_buf + beg, len, d_idx + idx_offsets[s], next - idx_offsets[s], flags, i,
+                          d_status ? d_status + 2 * i : nullptr);
+        c->h_results[i].reserved[0] = (uint32_t)rc;  // host-side launch status of this slot
+        if (rc != SJB200_SUCCESS) {
+            c->h_results[i].error = rc;
+            c->h_results[i].n_valid = 0;
+            if (d_status) {
+                const int32_t pair[2] = {rc, 0};
+                cudaMemcpyAsync(d_status + 2 * i, pair, sizeof pair, cudaMemcpyHostToDevice, c->stream);
+            }
+            if (rc > worst) worst = rc;
+        }
+    }
+    return worst;
+}
+
+int32_t sjb200_batch_run_device(sjb200_ctx *c, const uint8_t *d_buf, const uint64_t *seg_offsets, uint32_t first,
+                                uint32_t count, uint32_t *d_idx, const uint64_t *idx_offsets, uint64_t idx_capacity,
+                                uint32_t *seg_counts, int32_t *seg_errors, int32_t *seg_utf8, uint32_t flags) {
+    if (!c) return SJB200_UNINITIALIZED;
+    int32_t worst = sjb200_batch_run_device_async(c, d_buf, seg_offsets, first, count, d_idx, idx_offsets, idx_capacity,
+                                                  nullptr, flags);
+    if (worst == SJB200_UNINITIALIZED) return worst;
+    if (count > RESULT_SLOTS) return SJB200_CAPACITY;
+    CK(cudaStreamSynchronize(c->stream));
+    worst = SJB200_SUCCESS;
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t s = first + i;
+        const Stage1Result r = c->h_results[i];
+        const bool launched = r.reserved[0] == SJB200_SUCCESS || r.reserved[0] == 0;
+        if (seg_errors) seg_errors[s] = r.error;
+        if (seg_counts) seg_counts[s] = r.n_valid ? r.n : 0;
+        if (seg_utf8) seg_utf8[s] = (!launched || (flags & SJB200_FLAG_NO_UTF8)) ? -1 : r.utf8_error;
+        if (r.error > worst) worst = r.error;
+    }
+    return worst;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""Device-resident stage 1 over torch tensors (torch supplies device memory and streams; the compute is ours).
+
+This is the path the roofline metric times: input already in HBM, indexes left in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _native, errors
+
+
+@dataclass
+class DeviceResult:
+    error: int
+    n: int | None       # None where the reference leaves n_structural_indexes untouched
+    n_written: int
+    utf8_error: int
+
+
+class Stage1Context:
+    """One parser context per GPU; runs on torch's current stream of that device by default."""
+
+    def __init__(self, device: int | torch.device = 0, max_len: int = (1 << 32) - 1, max_len_host: int = 0,
+                 use_torch_stream: bool = True):
+        self._lib = _native.lib()
+        dev = torch.device("cuda", device) if isinstance(device, int) else device
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the stage-1 path has no CPU fallback")
+        self.device = dev
+        self._ctx = C.c_void_p()
+        rc = self._lib.sjb200_ctx_create(dev.index or 0, max_len, max_len_host, 0, C.byref(self._ctx))
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"sjb200_ctx_create failed: {errors.NAMES.get(rc, rc)}")
+        if use_torch_stream:
+            self.use_stream(torch.cuda.current_stream(dev))
+
+    def use_stream(self, stream: torch.cuda.Stream) -> None:
+        self._stream = stream
+        self._lib.sjb200_ctx_set_stream(self._ctx, C.c_void_p(stream.cuda_stream))
+
+    def set_warps(self, warps: int) -> None:
+        rc = self._lib.sjb200_ctx_set_warps(self._ctx, warps)
+        if rc != errors.SUCCESS:
+            raise ValueError("warps must be 0, 2, 4 or 8")
+
+    def close(self):
+        if self._ctx:
+            self._lib.sjb200_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- single document -------------------------------------------------------------------------
+    def enqueue(self, buf: torch.Tensor, out: torch.Tensor, flags: int = 0, length: int | None = None) -> int:
+        """Enqueue stage 1 of buf[:length] into out (uint32/int32 tensor).  Returns the launch status."""
+        assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
+        assert out.is_cuda and out.element_size() == 4 and out.is_contiguous()
+        n = buf.numel() if length is None else length
+        return self._lib.sjb200_stage1_device_async(self._ctx, buf.data_ptr(), n, out.data_ptr(), out.numel(), flags)
+
+    def finish(self) -> DeviceResult:
+        n = C.c_uint32(0xFFFFFFFF)
+        nw = C.c_uint32(0)
+        u8 = C.c_int32(0)
+        rc = self._lib.sjb200_stage1_finish(self._ctx, C.byref(n), C.byref(nw), C.byref(u8))
+        return DeviceResult(rc, None if n.value == 0xFFFFFFFF else n.value, nw.value, u8.value)
+
+    def index(self, buf: torch.Tensor, out: torch.Tensor, flags: int = 0, length: int | None = None) -> DeviceResult:
+        rc = self.enqueue(buf, out, flags, length)
+        if rc != errors.SUCCESS:
+            return DeviceResult(rc, None, 0, 0)
+        return self.finish()
+
+    def last_elapsed_ms(self) -> float:
+        return float(self._lib.sjb200_last_elapsed_ms(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self._lib.sjb200_launch_count(self._ctx))
+
+    def sync(self) -> None:
+        self._lib.sjb200_sync(self._ctx)
+
+    # -- NDJSON batches --------------------------------------------------------------------------
+    def split(self, buf: torch.Tensor, seg_bytes: int, max_segments: int = 4096) -> list[int]:
+        assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
+        offs = (C.c_uint64 * (max_segments + 1))()
+        nseg = C.c_uint32(0)
+        rc = self._lib.sjb200_batch_split_device(self._ctx, buf.data_ptr(), buf.numel(), seg_bytes, offs, max_segments,
+                                                 C.byref(nseg))
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"batch split failed: {errors.NAMES.get(rc, rc)}")
+        return [int(offs[i]) for i in range(nseg.value + 1)]
+
+    def run_segments(self, buf: torch.Tensor, seg_offsets: list[int], out: torch.Tensor, flags: int = 0,
+                     first: int = 0, count: int | None = None):
+        """Index segments [first, first+count) back to back.  Segment s writes at out[idx_offsets[s]:]."""
+        nseg = len(seg_offsets) - 1
+        if count is None:
+            count = nseg - first
+        offs = (C.c_uint64 * (nseg + 1))(*seg_offsets)
+        idx_offsets = [0] * (nseg + 1)
+        for s in range(first, first + count):
+            idx_offsets[s + 1] = idx_offsets[s] + (seg_offsets[s + 1] - seg_offsets[s]) + 3
+        ioffs = (C.c_uint64 * (nseg + 1))(*idx_offsets)
+        counts = (C.c_uint32 * nseg)()
+        errs = (C.c_int32 * nseg)()
+        u8 = (C.c_int32 * nseg)()
+        worst = self._lib.sjb200_batch_run_device(self._ctx, buf.data_ptr(), offs, first, count, out.data_ptr(), ioffs,
+                                                  out.numel(), counts, errs, u8, flags)
+        sl = slice(first, first + count)
+        return worst, list(counts)[sl], list(errs)[sl], list(u8)[sl], idx_offsets[first:first + count + 1]
+
+    def run_segments_async(self, buf: torch.Tensor, seg_offsets: list[int], out: torch.Tensor, status: torch.Tensor,
+                           flags: int = 0) -> int:
+        """Enqueue every segment without waiting; segment s leaves (error, n) at status[s] (int32 [nseg, 2], device)."""
+        nseg = len(seg_offsets) - 1
+        assert status.is_cuda and status.dtype == torch.int32 and status.numel() >= 2 * nseg and status.is_contiguous()
+        key = (tuple(seg_offsets), out.numel())
+        cached = getattr(self, "_seg_cache", None)
+        if cached is None or cached[0] != key:
+            offs = (C.c_uint64 * (nseg + 1))(*seg_offsets)
+            idx_offsets = [0] * (nseg + 1)
+            for s in range(nseg):
+                idx_offsets[s + 1] = idx_offsets[s] + (seg_offsets[s + 1] - seg_offsets[s]) + 3
+            ioffs = (C.c_uint64 * (nseg + 1))(*idx_offsets)
+            self._seg_cache = (key, offs, ioffs, idx_offsets)
+        _, offs, ioffs, _ = self._seg_cache
+        return self._lib.sjb200_batch_run_device_async(self._ctx, buf.data_ptr(), offs, 0, nseg, out.data_ptr(), ioffs,
+                                                       out.numel(), status.data_ptr(), flags)

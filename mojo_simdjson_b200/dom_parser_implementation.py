@@ -1,0 +1,89 @@
+"""Host-side mirror of the reference's parser facade for the stage-1 path.
+
+Reference: src/mojo_simdjson/include/generic/dom_parser_implementation.mojo:15-89.  Same field names, same
+call (`stage1(buffer) -> ErrorType`), same error behaviour; the line that called
+JsonStructuralIndexer.index[128] (:69) calls libsimdjson_b200.so instead.  Stage 2 is not part of this path:
+a consumer reads `buf`, `length`, `structural_indexes[0 .. n+2]`, `n_structural_indexes` and
+`next_structural_index` exactly as the reference's JsonIterator does (json_iterator.mojo:28-38,256-288).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native, errors
+
+DEFAULT_MAX_LEN = 64 << 20
+
+
+class DomParserImplementation:
+    """Stage-1 half of the reference's DomParserImplementation, backed by the B200 kernel."""
+
+    def __init__(self, device: int = 0, max_len: int = DEFAULT_MAX_LEN, validate_utf8: bool = False):
+        self._lib = _native.lib()
+        if self._lib.sjb200_device_count() <= 0:
+            raise RuntimeError("no CUDA device: the stage-1 path has no CPU fallback")
+        self.buf: np.ndarray | None = None          # buffer passed to stage 1 (kept alive for stage 2)
+        self.length = 0
+        self.n_structural_indexes = 0
+        self.structural_indexes = np.zeros(0, dtype=np.uint32)
+        self.next_structural_index = 0
+        self.utf8_error = 0                          # not in the reference: its Utf8Checker is a stub
+        self._capacity = 0
+        self._max_depth = 100
+        self._max_len = max_len
+        self._flags = _native.FLAG_VALIDATE_UTF8 if validate_utf8 else 0
+        self._ctx = C.c_void_p()
+        rc = self._lib.sjb200_ctx_create(device, max_len, max_len, 0, C.byref(self._ctx))
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"sjb200_ctx_create failed: {errors.NAMES.get(rc, rc)}")
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.sjb200_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def max_depth(self) -> int:
+        return self._max_depth
+
+    def capacity(self) -> int:
+        return self._capacity
+
+    def allocate(self, amount: int) -> None:
+        # reference :85-89 resizes to `amount` entries and then writes the 3-entry trailer past the end;
+        # we allocate the 3 extra entries the trailer needs
+        if self.structural_indexes.size < amount + 3:
+            self.structural_indexes = np.zeros(amount + 3, dtype=np.uint32)
+        self._capacity = amount
+
+    def stage1(self, buffer) -> int:
+        """reference :59-69 -- accepts str / bytes / uint8 ndarray, returns the error code."""
+        if isinstance(buffer, str):
+            buffer = buffer.encode("utf-8")
+        if isinstance(buffer, (bytes, bytearray, memoryview)):
+            buffer = np.frombuffer(bytes(buffer), dtype=np.uint8)
+        buffer = np.ascontiguousarray(buffer, dtype=np.uint8)
+        n_bytes = int(buffer.size)
+        self.allocate(n_bytes)
+        self.buf = buffer
+        self.length = n_bytes
+        if n_bytes > self._max_len:
+            return errors.CAPACITY
+        n = C.c_uint32(self.n_structural_indexes)
+        u8 = C.c_int32(0)
+        rc = self._lib.sjb200_stage1(self._ctx, buffer.ctypes.data if n_bytes else None, n_bytes,
+                                     self.structural_indexes.ctypes.data, self.structural_indexes.size,
+                                     C.byref(n), C.byref(u8), self._flags)
+        self.utf8_error = int(u8.value)
+        if rc in (errors.SUCCESS, errors.EMPTY, errors.UTF8_ERROR) and n_bytes:
+            # the reference assigns these only past its early returns (json_structural_indexer.mojo:160-174)
+            self.n_structural_indexes = int(n.value)
+            self.next_structural_index = 0
+        return rc

@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA stage 1 (through the C ABI) against the CPU oracle, bit-exact.
+
+Run on a B200 with `pytest -m gpu`.  Indexes, n, trailer, verdicts and the UTF-8 verdict must all be identical
+to the oracle's on the same inputs; at full size (1 GiB) the comparison is a digest of the index stream plus
+size-independent properties.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from mojo_simdjson_b200 import device
+
+    ctx = device.Stage1Context(0, max_len=(1 << 32) - 1)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def parser():
+    from mojo_simdjson_b200.dom_parser_implementation import DomParserImplementation
+
+    p = DomParserImplementation(0, max_len=8 << 20)
+    yield p
+    p.close()
+
+
+class Scratch:
+    """Reusable device buffers; inputs are placed at a chosen misalignment inside the allocation."""
+
+    def __init__(self, nbytes):
+        self.inp = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+        self.out = torch.empty(nbytes + 16, dtype=torch.int32, device="cuda")
+
+    def put(self, data: bytes, mis: int):
+        a = np.frombuffer(data, dtype=np.uint8)
+        # hostile bytes around the document: the kernel must never let them leak in
+        self.inp[: mis + len(data) + 64].fill_(0x22)
+        view = self.inp[mis : mis + len(data)]
+        view.copy_(torch.from_numpy(a.copy()))
+        return view
+
+
+@pytest.fixture(scope="module")
+def scratch():
+    return Scratch(4 << 20)
+
+
+def run_device(dev, scratch, data: bytes, mis=0, flags=0, warps=0, cap=None):
+    dev.set_warps(warps)
+    view = scratch.put(data, mis)
+    out = scratch.out if cap is None else scratch.out[:cap]
+    scratch.out[: len(data) + 8].fill_(-1)
+    res = dev.index(view, out, flags)
+    dev.set_warps(0)
+    return res, scratch.out
+
+
+def assert_same(res, out_t, want, cap=None):
+    assert res.error == want.error
+    assert res.n == want.n
+    if want.error != oracle.CAPACITY:
+        assert res.n_written == want.n_written
+        keep = want.indexes.size
+        got = out_t[:keep].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want.indexes)
+    assert res.utf8_error == want.utf8_error
+
+
+# ------------------------------------------------------------------------------------------------
+# config 1: the reference's own fixtures, through the reference-shaped facade (host buffers)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fx", cases.golden_fixtures(), ids=lambda f: f["file"])
+def test_reference_fixtures_through_facade(parser, fx):
+    """tests/test_stage_1.mojo:85-96 + :43-82 restated against the drop-in."""
+    err = parser.stage1(fx["input"])
+    assert err == 0, "unexpected error code"
+    n = parser.n_structural_indexes
+    got = [int(x) for x in parser.structural_indexes[:n]]
+    assert all(a < b for a, b in zip(got, got[1:]))
+    mask = [" "] * len(fx["mask"])
+    for i in got:
+        mask[i] = "1"
+    if fx["harness_negative"]:
+        assert "".join(mask) != fx["mask"]
+    else:
+        assert "".join(mask) == fx["mask"]
+    ln = len(fx["input"].encode("utf-8"))
+    assert list(parser.structural_indexes[n : n + 3]) == [ln, ln, 0]
+    assert parser.next_structural_index == 0
+
+
+@pytest.mark.parametrize("case", cases.KNOWN_ANSWERS, ids=lambda c: repr(c)[:24])
+def test_known_answers_through_facade(parser, case):
+    data, err, n, idx = case
+    parser.n_structural_indexes = 777  # sentinel: must survive the reference's early-return paths
+    got = parser.stage1(data)
+    assert got == err
+    if n is None:
+        assert parser.n_structural_indexes == 777
+    else:
+        assert parser.n_structural_indexes == n
+        assert list(parser.structural_indexes[n : n + 3]) == [len(data), len(data), 0]
+    if idx:
+        assert [int(x) for x in parser.structural_indexes[: len(idx)]] == idx
+
+
+def test_host_path_matches_oracle_on_corpus(parser):
+    for name, data in cases.adversarial_cases(tile_bytes=(4096,))[::7]:
+        want = oracle.stage1(data)
+        parser.n_structural_indexes = 0xFFFFFFFF
+        err = parser.stage1(data)
+        assert err == want.error, name
+        if want.n is not None:
+            assert parser.n_structural_indexes == want.n, name
+        assert np.array_equal(parser.structural_indexes[: want.indexes.size], want.indexes), name
+        assert parser.utf8_error == want.utf8_error, name
+
+
+def test_validate_utf8_flag_through_facade():
+    from mojo_simdjson_b200.dom_parser_implementation import DomParserImplementation
+
+    p = DomParserImplementation(0, max_len=1 << 20, validate_utf8=True)
+    try:
+        assert p.stage1(b'["\xc0\x80"]') == 11
+        assert p.stage1(b'"\xff') == 15
+        assert p.stage1(b'"\xff\x01"') == 14
+        assert p.stage1('["héllo"]') == 0
+    finally:
+        p.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5: adversarial set, device-resident path, every tile shape, aligned and misaligned input
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("warps", [2, 4, 8])
+def test_adversarial_corpus_device(dev, scratch, warps):
+    tiles = tuple(sorted({warps * 2048, 4096}))
+    corpus = cases.adversarial_cases(tile_bytes=tiles)
+    if warps != 2:
+        corpus = corpus[::3]
+    for k, (name, data) in enumerate(corpus):
+        if not data:
+            continue
+        want = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+        for mis in ((0, 5) if k % 4 == 0 else (0,)):
+            res, out = run_device(dev, scratch, data, mis=mis, warps=warps)
+            try:
+                assert_same(res, out, want)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"case {name} mis={mis} warps={warps}") from e
+
+
+def test_every_misalignment(dev, scratch):
+    data = b'{"k":"v\\"x","a":[1,2,3],"u":"\xe2\x82\xac"}' * 300
+    want = oracle.stage1(data)
+    for mis in range(16):
+        res, out = run_device(dev, scratch, data, mis=mis, warps=2)
+        assert_same(res, out, want)
+
+
+def test_flags(dev, scratch):
+    bad = b'["\xc0\x80"]' * 10
+    res, _ = run_device(dev, scratch, bad, flags=1)
+    assert res.error == 11 and res.utf8_error == 1
+    res, _ = run_device(dev, scratch, bad, flags=0)
+    assert res.error == 0 and res.utf8_error == 1
+    res, _ = run_device(dev, scratch, bad, flags=4)  # NO_UTF8: verdict not computed
+    assert res.error == 0 and res.utf8_error == -1
+    assert dev.index(scratch.inp[:0], scratch.out).error == 13  # len == 0 -> EMPTY, no launch
+
+
+def test_capacity(dev, scratch):
+    data = b"[1,2,3]"
+    res, out = run_device(dev, scratch, data, cap=10)
+    assert res.error == 0 and res.n == 7
+    res, out = run_device(dev, scratch, data, cap=9)
+    assert res.error == 1 and res.n is None
+    # nothing may be written past the capacity
+    big = b"[" + b"1," * 5000 + b"1]"
+    scratch.out[:20000].fill_(-1)
+    res, out = run_device(dev, scratch, big, cap=100)
+    assert res.error == 1
+    assert int((scratch.out[100:20000] != -1).sum()) == 0
+
+
+def test_dense_tile_takes_direct_path(dev, scratch):
+    data = b"[" + b"1," * 100000 + b"1]"  # every byte structural: > 0.5 per byte, bypasses staging
+    want = oracle.stage1(data, impl="fast")
+    for warps in (2, 8):
+        res, out = run_device(dev, scratch, data, warps=warps)
+        assert_same(res, out, want)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.sampled_from(list(cases.NASTY)), min_size=1, max_size=12000), st.integers(0, 15))
+def test_fuzz_nasty_device(dev, scratch, xs, mis):
+    data = bytes(xs)
+    res, out = run_device(dev, scratch, data, mis=mis, warps=2)
+    assert_same(res, out, oracle.stage1(data))
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.binary(min_size=1, max_size=6000), st.integers(0, 15))
+def test_fuzz_binary_device(dev, scratch, data, mis):
+    res, out = run_device(dev, scratch, data, mis=mis, warps=2)
+    assert_same(res, out, oracle.stage1(data))
+
+
+def test_repeated_calls_reuse_descriptors(dev, scratch):
+    """Generation-tagged look-back descriptors: back-to-back calls with different inputs must not interfere."""
+    a = (b'{"a":"' + b"x" * 5000 + b'"}') * 40
+    b = b'"' + b"\\" * 70001 + b'" 1'
+    wa, wb = oracle.stage1(a, impl="fast"), oracle.stage1(b, impl="fast")
+    for _ in range(20):
+        res, out = run_device(dev, scratch, a, warps=2)
+        assert_same(res, out, wa)
+        res, out = run_device(dev, scratch, b, warps=2)
+        assert_same(res, out, wb)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs 2-4: synthetic workloads
+# ------------------------------------------------------------------------------------------------
+def test_twitter_like_631k(dev):
+    from mojo_simdjson_b200 import synth
+
+    doc = synth.twitter_like()
+    assert doc.size == 631_515
+    want = oracle.stage1(doc, impl="fast")
+    assert want.error == 0
+    inp = torch.from_numpy(doc).cuda()
+    out = torch.empty(doc.size + 3, dtype=torch.int32, device="cuda")
+    for warps in (0, 2, 4, 8):
+        dev.set_warps(warps)
+        out.fill_(-1)
+        res = dev.index(inp, out)
+        assert_same(res, out, want)
+    dev.set_warps(0)
+
+
+def test_document_64mib_full_compare(dev):
+    from mojo_simdjson_b200 import synth
+
+    size = 64 << 20
+    doc = synth.status_array(size)
+    want = oracle.stage1(doc, impl="fast", cap=size // 3)
+    assert want.error == 0
+    inp = torch.from_numpy(doc).cuda()
+    out = torch.empty(size // 3, dtype=torch.int32, device="cuda")
+    for warps in (2, 8):
+        dev.set_warps(warps)
+        out.fill_(-1)
+        res = dev.index(inp, out)
+        assert_same(res, out, want)
+    dev.set_warps(0)
+    # error injected far into the document: verdict parity at scale
+    bad = doc.copy()
+    bad[size - 1000] = 0x22
+    want = oracle.stage1(bad, impl="fast", cap=size // 3)
+    inp.copy_(torch.from_numpy(bad))
+    res = dev.index(inp, out)
+    assert res.error == want.error and res.n == want.n and res.n_written == want.n_written
+
+
+@pytest.mark.skipif(os.environ.get("SJB200_SKIP_1GIB") == "1", reason="SJB200_SKIP_1GIB=1")
+def test_document_1gib_digest_and_properties(dev):
+    """BASELINE.json config 3 at full size: digest of the index stream vs the oracle + domain properties."""
+    from mojo_simdjson_b200 import synth
+
+    size = 1 << 30
+    doc = synth.status_array(size)
+    cap = size // 4
+    want = oracle.stage1(doc, impl="fast", cap=cap)
+    assert want.error == 0
+    inp = torch.from_numpy(doc).cuda()
+    out = torch.empty(cap, dtype=torch.int32, device="cuda")
+    res = dev.index(inp, out)
+    assert res.error == 0 and res.n == want.n and res.utf8_error == 0
+    n = res.n
+    got = out[: n + 3].cpu().numpy().view(np.uint32)
+    assert oracle.index_digest(got) == oracle.index_digest(want.indexes)
+    # properties: strictly ascending, every index on a structural byte or a scalar/string start, trailer
+    assert bool((got[1:n] > got[: n - 1]).all())
+    assert list(got[n : n + 3]) == [size, size, 0]
+    first_bytes = doc[got[:n]]
+    assert not np.isin(first_bytes, np.frombuffer(b" \n\t\r", dtype=np.uint8)).any()
+    # idempotence: a second run over the same buffer gives the same stream
+    out2 = torch.empty(cap, dtype=torch.int32, device="cuda")
+    res2 = dev.index(inp, out2)
+    assert res2.n == n and bool(torch.equal(out[: n + 3], out2[: n + 3]))
+
+
+def test_ndjson_batch_segments(dev):
+    """Config 4 in miniature: cut at newlines, every segment == an independent reference call."""
+    from mojo_simdjson_b200 import synth
+
+    size = 48 << 20
+    batch = synth.ndjson(size)
+    inp = torch.from_numpy(batch).cuda()
+    seg_bytes = 5 << 20
+    offs = dev.split(inp, seg_bytes)
+    assert offs[0] == 0 and offs[-1] == size
+    host_offs = (C.c_uint64 * 64)()
+    nseg = C.c_uint32(0)
+    from mojo_simdjson_b200 import _native
+
+    rc = _native.lib().sjb200_batch_split_host(batch.ctypes.data, size, seg_bytes, host_offs, 63, C.byref(nseg))
+    assert rc == 0 and [int(host_offs[i]) for i in range(nseg.value + 1)] == offs
+    for a, b in zip(offs, offs[1:]):
+        assert b > a and b - a <= 2 * seg_bytes and batch[b - 1] == 0x0A
+    out = torch.empty(size + 3 * len(offs), dtype=torch.int32, device="cuda")
+    out.fill_(-1)
+    worst, counts, errs, u8, idx_offs = dev.run_segments(inp, offs, out)
+    assert worst == 0
+    host = out.cpu().numpy().view(np.uint32)
+    for s in range(len(offs) - 1):
+        seg = batch[offs[s] : offs[s + 1]]
+        want = oracle.stage1(seg, impl="fast")
+        assert errs[s] == want.error == 0
+        assert counts[s] == want.n
+        assert u8[s] == 0
+        got = host[idx_offs[s] : idx_offs[s] + want.n + 3]
+        assert np.array_equal(got, want.indexes)
