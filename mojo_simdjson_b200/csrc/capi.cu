@@ -153,6 +153,7 @@ __global__ void split_kernel(const uint8_t *buf, uint64_t len, uint64_t seg_byte
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 int32_t sjb200_version(void) { return SJB200_ABI_VERSION; }
@@ -460,3 +461,4 @@ int32_t sjb200_batch_run_device(sjb200_ctx *c, const uint8_t *d_buf, const uint6
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

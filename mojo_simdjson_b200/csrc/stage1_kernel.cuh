@@ -430,7 +430,8 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
     const uint32_t v0 = (uint32_t)(g0 - (int64_t)P.mis); // index value of bit 0 of the chunk
     if (total <= (uint32_t)Cfg::STAGE_CAP) {
         uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
-        const uint32_t a = base & 3u;                    // keep shared and global 16-byte phases equal
+        // keep shared and global 16-byte phases equal (the output pointer itself may be only 4-byte aligned)
+        const uint32_t a = (base + (uint32_t)((reinterpret_cast<uintptr_t>(P.out) >> 2) & 3u)) & 3u;
         uint32_t o = a + my;
         uint32_t bits = st_lo;
         while (bits) {
@@ -444,20 +445,20 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
         }
         __syncthreads();  // E
         // coalesced copy-out: vector v holds staged entries [4v, 4v+4) = global entries gbase + 4v ..
-        const uint64_t gbase = (uint64_t)base - a;       // multiple of 4
+        const int64_t gbase = (int64_t)base - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
         const uint32_t end = a + total;
         const uint32_t nvec = (end + 3u) >> 2;
         for (uint32_t v = tid; v < nvec; v += Cfg::THREADS) {
             const uint4 q = reinterpret_cast<const uint4 *>(stage)[v];
             const uint32_t j = 4u * v;
-            const uint64_t g = gbase + j;
-            if (j >= a && j + 4u <= end && g + 4u <= P.cap) {
+            const int64_t g = gbase + (int64_t)j;
+            if (j >= a && j + 4u <= end && (uint64_t)(g + 4) <= P.cap) {
                 *reinterpret_cast<uint4 *>(P.out + g) = q;
             } else {
                 const uint32_t vals[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    if (j + i >= a && j + i < end && g + i < P.cap) P.out[g + i] = vals[i];
+                    if (j + i >= a && j + i < end && (uint64_t)(g + i) < P.cap) P.out[g + i] = vals[i];
             }
         }
     } else {
