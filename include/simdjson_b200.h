@@ -77,7 +77,7 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *ctx);
 
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
 int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
-/* Force the tile shape: warps per tile in {2,4,8}, 0 = choose from the document size. */
+/* Force the tile shape: warps per tile in {2,4,8,16,32} (2 KiB per warp), 0 = choose from the document size. */
 int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
 
 /*

@@ -39,7 +39,7 @@ struct sjb200_ctx {
     uint8_t *d_in = nullptr;        // host-path input staging on the device
     uint32_t *d_out = nullptr;      // host-path output on the device
     uint64_t d_out_cap = 0;
-    uint64_t *desc1 = nullptr, *desc2 = nullptr;
+    uint64_t *desc = nullptr;           // look-back descriptors, one 8-byte word per tile
     uint32_t max_tiles = 0;
     uint32_t *ticket = nullptr;
     Stage1Result *h_results = nullptr;  // mapped pinned, RESULT_SLOTS entries
@@ -63,6 +63,17 @@ cudaError_t launch_cfg(const Stage1Params &p, cudaStream_t s) {
     stage1_kernel<WARPS, UTF8><<<p.ntiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
 }
+template <int WARPS>
+cudaError_t prepare_cfg() {
+    using Cfg = TileCfg<WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(stage1_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(stage1_kernel<WARPS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
+bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 32; }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (c->forced_warps) return c->forced_warps;
@@ -70,7 +81,7 @@ int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (env < 0) {
         const char *e = getenv("SJB200_WARPS");
         env = e ? atoi(e) : 0;
-        if (env != 2 && env != 4 && env != 8) env = 0;
+        if (!valid_warps(env)) env = 0;
     }
     if (env) return env;
     // small documents: smaller tiles so that the work spreads over all 148 SMs
@@ -90,13 +101,15 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     p.len = (uint32_t)len;
     p.out = d_idx;
     p.cap = cap;
-    p.desc1 = c->desc1;
-    p.desc2 = c->desc2;
+    p.desc = c->desc;
     p.ticket = c->ticket;
     p.result = c->d_results + slot;
     p.dev_status = d_status;
-    c->gen++;
-    if ((c->gen & 0x0FFFFFFFu) == 0) c->gen++;  // generation 0 is the cleared state of the descriptors
+    c->gen = (c->gen + 1) & GEN_MASK;
+    if (c->gen == 0) {  // the 20-bit generation wrapped: clear the descriptors once (stream ordered), restart at 1
+        cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
+        c->gen = 1;
+    }
     p.gen = c->gen;
     p.flags = flags;
     const int warps = pick_warps(c, p.alen);
@@ -108,6 +121,8 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     cudaError_t e;
     if (c->timed) cudaEventRecord(c->ev0, c->stream);
     switch (warps) {
+    case 32: e = utf8 ? launch_cfg<32, true>(p, c->stream) : launch_cfg<32, false>(p, c->stream); break;
+    case 16: e = utf8 ? launch_cfg<16, true>(p, c->stream) : launch_cfg<16, false>(p, c->stream); break;
     case 8: e = utf8 ? launch_cfg<8, true>(p, c->stream) : launch_cfg<8, false>(p, c->stream); break;
     case 4: e = utf8 ? launch_cfg<4, true>(p, c->stream) : launch_cfg<4, false>(p, c->stream); break;
     default: e = utf8 ? launch_cfg<2, true>(p, c->stream) : launch_cfg<2, false>(p, c->stream); break;
@@ -178,12 +193,10 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     c->own_stream = (e == cudaSuccess);
     c->max_tiles = (uint32_t)((max_len + 16 + MIN_TILE - 1) / MIN_TILE + 1);
-    if (e == cudaSuccess) e = cudaMalloc(&c->desc1, (size_t)c->max_tiles * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&c->desc2, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->desc, (size_t)c->max_tiles * 8);
     if (e == cudaSuccess) e = cudaMalloc(&c->ticket, 256);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_split, 8 * 4096);
-    if (e == cudaSuccess) e = cudaMemset(c->desc1, 0, (size_t)c->max_tiles * 8);
-    if (e == cudaSuccess) e = cudaMemset(c->desc2, 0, (size_t)c->max_tiles * 8);
+    if (e == cudaSuccess) e = cudaMemset(c->desc, 0, (size_t)c->max_tiles * 8);
     if (e == cudaSuccess) e = cudaMemset(c->ticket, 0, 256);
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_results, sizeof(Stage1Result) * RESULT_SLOTS, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->d_results, c->h_results, 0);
@@ -194,12 +207,12 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) {
-        // the staged tile needs no opt-in (< 48 KiB) but ask for the shared-memory carveout we want
-        cudaFuncSetAttribute(stage1_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(stage1_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        e = cudaDeviceSynchronize();
-    }
+    if (e == cudaSuccess) e = prepare_cfg<2>();
+    if (e == cudaSuccess) e = prepare_cfg<4>();
+    if (e == cudaSuccess) e = prepare_cfg<8>();
+    if (e == cudaSuccess) e = prepare_cfg<16>();
+    if (e == cudaSuccess) e = prepare_cfg<32>();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         const int32_t code = cuda_err(e);
         sjb200_ctx_destroy(c);
@@ -216,8 +229,7 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
-    cudaFree(c->desc1);
-    cudaFree(c->desc2);
+    cudaFree(c->desc);
     cudaFree(c->ticket);
     cudaFree(c->d_split);
     if (c->h_results) cudaFreeHost(c->h_results);
@@ -239,7 +251,7 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *c, void *cuda_stream) {
 
 int32_t sjb200_ctx_set_warps(sjb200_ctx *c, int32_t warps) {
     if (!c) return SJB200_UNINITIALIZED;
-    if (warps != 0 && warps != 2 && warps != 4 && warps != 8) return SJB200_UNEXPECTED_ERROR;
+    if (warps != 0 && !valid_warps(warps)) return SJB200_UNEXPECTED_ERROR;
     c->forced_warps = warps;
     return SJB200_SUCCESS;
 }

@@ -259,130 +259,181 @@ SJ_HD uint64_t prefix_xor64(uint64_t x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Carry algebra.  The state entering a span of bytes is (e, s, p):
-//   e = its first byte is escaped, s = it starts inside a string, p = the byte before it is a
-//   non-quote scalar.  What a span does to that state depends on e only (never on s or p), so a span
-//   is summarised, for e = 0 and e = 1 separately, by (e_out, s_flip, p_out): 6 bits + an identity flag.
-//   bit 0/3: e_out   bit 1/4: s_flip   bit 2/5: p_out   (for e_in = 0 / 1);   bit 6: identity
-// Composition is associative; it is used across the warps of a tile and across tiles (decoupled
-// look-back).  Replaces the three sequential 1-bit carries of the reference.
+// Carries.  The reference threads three 1-bit carries through its 64-byte blocks:
+//   e = the first byte is escaped, p = the previous byte is a non-quote scalar, s = inside a string.
+// e and p depend only on the few bytes just before a position, so every lane / warp / tile resolves
+// them LOCALLY by looking at the preceding bytes (they are in shared memory anyway); only when a
+// backslash run covers the whole look-behind window does it ask its predecessor.  The single carry
+// that needs a global scan is s, the parity of all unescaped quotes before the position.
 // ------------------------------------------------------------------------------------------------
-typedef uint32_t SpanFn;
-static const SpanFn SPAN_IDENT = 1u << 6;
-
-SJ_HD SpanFn span_make(uint32_t eo0, uint32_t fl0, uint32_t po0, uint32_t eo1, uint32_t fl1, uint32_t po1) {
-    return (eo0 & 1) | ((fl0 & 1) << 1) | ((po0 & 1) << 2) | ((eo1 & 1) << 3) | ((fl1 & 1) << 4) | ((po1 & 1) << 5);
+SJ_HD uint32_t byte_is_scalar(uint32_t c) {  // !(op | whitespace), reference json_character_block.mojo:22-23
+    const bool ws = c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0D;
+    const bool op = c == 0x2C || c == 0x3A || c == 0x5B || c == 0x5D || c == 0x7B || c == 0x7D || c == 0x0C || c == 0x1A;
+    return !(ws || op);
 }
-// constant function: whatever comes in, the state after is (e, s, p) -- s relative to "outside a string"
-SJ_HD SpanFn span_const(uint32_t e, uint32_t s, uint32_t p) { return span_make(e, s, p, e, s, p); }
 
-SJ_HD SpanFn span_compose(SpanFn older, SpanFn newer) {  // apply older first, then newer
-    if (older & SPAN_IDENT) return newer;
-    if (newer & SPAN_IDENT) return older;
-    SpanFn r = 0;
-    for (int e = 0; e < 2; e++) {
-        const uint32_t a = (older >> (3 * e)) & 7;
-        const uint32_t b = (newer >> (3 * (a & 1))) & 7;
-        const uint32_t o = (b & 1) | ((a ^ b) & 2) | (b & 4);
-        r |= o << (3 * e);
+struct PrevState {
+    uint32_t e, p;       // carries entering the position
+    uint32_t unresolved; // bit0: e needs more look-behind, bit1: p needs more look-behind
+};
+// bsm: bit i set iff the byte at distance i+1 before the position is a backslash (i < nvalid, higher bits 0);
+// c1: the byte just before the position.
+SJ_HD PrevState prev_state(uint32_t bsm, int nvalid, uint32_t c1) {
+    PrevState r;
+    const int r1 = ffs32(~bsm) - 1;            // backslash run ending at byte -1   (32 if bsm is all ones)
+    const int r2 = ffs32(~(bsm >> 1)) - 1;     // backslash run ending at byte -2
+    r.e = (uint32_t)r1 & 1u;
+    r.unresolved = (r1 < 0 || r1 >= nvalid) ? 1u : 0u;
+    if (c1 == 0x22) {
+        r.p = (uint32_t)r2 & 1u;               // an escaped quote is an ordinary scalar character
+        if (r2 < 0 || r2 >= nvalid - 1) r.unresolved |= 2u;
+    } else {
+        r.p = byte_is_scalar(c1);
     }
     return r;
 }
 
-struct CarryState {
-    uint32_t e, s, p;
-};
-SJ_HD CarryState span_apply(SpanFn f, CarryState in) {
-    if (f & SPAN_IDENT) return in;
-    const uint32_t a = (f >> (3 * (in.e & 1))) & 7;
-    CarryState o;
-    o.e = a & 1;
-    o.s = in.s ^ ((a >> 1) & 1);
-    o.p = (a >> 2) & 1;
-    return o;
+// Slow path: walk back over a long backslash run.  before[-1] is the last byte of the run, at most `limit`
+// bytes may be read.  Returns the run length (== limit if it covers everything readable).
+SJ_HD uint32_t backslash_run_before(const uint8_t *before, uint32_t limit) {
+    uint32_t r = 0;
+    while (r < limit && before[-(int)(r + 1)] == 0x5C) r++;
+    return r;
 }
-SJ_HD uint32_t carry_pack(CarryState c) { return (c.e & 1) | ((c.s & 1) << 1) | ((c.p & 1) << 2); }
-SJ_HD CarryState carry_unpack(uint32_t v) {
-    CarryState c;
-    c.e = v & 1;
-    c.s = (v >> 1) & 1;
-    c.p = (v >> 2) & 1;
-    return c;
-}
+// escapedness of the byte following a run of `run` backslashes whose first backslash has escapedness e0
+SJ_HD uint32_t escaped_after_run(uint32_t run, uint32_t e0) { return (run & 1u) ^ e0; }
 
 // ------------------------------------------------------------------------------------------------
-// Lane-level escape summary and in-warp resolution from two ballots
+// In-warp escape resolution from two ballots
 //   A = ballot(lane is all backslashes), O = ballot(parity of the lane's trailing backslash run)
 // ------------------------------------------------------------------------------------------------
 SJ_HD bool lane_all_backslash(uint64_t bs) { return bs == ~0ull; }
 SJ_HD uint32_t lane_trailing_run_parity(uint64_t bs) { return (uint32_t)clz64(~bs) & 1u; }
 
-// e_in of `lane` (0..32; 32 = the carry leaving the warp) assuming the warp's own e_in is 0.
-// *lead = every earlier lane of the warp is all backslashes, i.e. the warp's e_in passes straight through.
-SJ_HD uint32_t warp_lane_e_in(uint32_t A, uint32_t O, int lane, bool *lead) {
+// e_in of `lane` (0..32; 32 = the carry leaving the warp) given the warp's own e_in.
+// A lane made only of backslashes passes its e_in through (64 is even).
+SJ_HD uint32_t warp_lane_e_in(uint32_t A, uint32_t O, int lane, uint32_t e_warp) {
     const uint32_t below = ~A & (lane >= 32 ? 0xFFFFFFFFu : ((1u << lane) - 1u));
-    *lead = (below == 0);
-    if (below == 0) return 0;
+    if (below == 0) return e_warp & 1u;
     const int j = 31 - clz32(below);
     return (O >> j) & 1u;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Everything a lane keeps between the phases of a tile
+// Lane results.  Everything is exact relative to the start of the warp except the in-string parity:
+// the structural mask is produced for both values of "the warp starts inside a string".
 // ------------------------------------------------------------------------------------------------
 struct LaneMasks {
     uint64_t bs, rq, op, ws, ctl;
-    uint64_t quote;   // unescaped quotes (under the e_in assumed so far)
-    uint64_t ps;      // prefix xor of quote (in_string relative to the chunk start)
-    uint64_t flipq;   // the one raw quote whose escapedness flips if the warp's e_in turns out to be 1
 };
-
-// phase 1b: after the lane knows its e_in (assuming warp e_in = 0)
-SJ_HD void lane_resolve_quotes(LaneMasks &m, uint32_t e_in, bool lead) {
-    const uint64_t esc = escaped_mask(m.bs, (uint64_t)e_in);
-    m.quote = m.rq & ~esc;
-    m.ps = prefix_xor64(m.quote);
-    // first non-backslash byte of a leading lane: its escapedness is the warp carry xor run parity
-    m.flipq = (lead && m.bs != ~0ull) ? (m.rq & ~m.bs & (m.bs + 1)) : 0;
-}
-// applied only when the warp's e_in is really 1
-SJ_HD void lane_apply_escape_carry(LaneMasks &m) {
-    m.quote ^= m.flipq;
-    m.ps ^= (0 - m.flipq);  // flips every position >= the quote
-}
-
-SJ_HD uint64_t lane_nonquote_scalar(const LaneMasks &m) { return ~(m.op | m.ws) & ~m.quote; }
-
-struct LaneOut {
-    uint64_t structural;
-    uint32_t unescaped_err;
+struct LaneQuotes {
+    uint64_t quote;  // unescaped quotes
+    uint64_t ps;     // prefix xor of quote: in_string relative to the chunk start
+    uint64_t nqs;    // non-quote scalar
 };
-// phase 2: s_in = the chunk starts inside a string, p_in = previous byte is a non-quote scalar
-SJ_HD LaneOut lane_structurals(const LaneMasks &m, uint32_t s_in, uint32_t p_in) {
-    const uint64_t in_string = m.ps ^ (0 - (uint64_t)(s_in & 1));
+SJ_HD LaneQuotes lane_quotes(const LaneMasks &m, uint32_t e_in) {
+    LaneQuotes q;
+    const uint64_t esc = escaped_mask(m.bs, (uint64_t)(e_in & 1));
+    q.quote = m.rq & ~esc;
+    q.ps = prefix_xor64(q.quote);
+    q.nqs = ~(m.op | m.ws) & ~q.quote;
+    return q;
+}
+struct LaneDual {
+    uint64_t m0, m1;      // structural bits if the warp starts outside / inside a string
+    uint32_t u0, u1;      // unescaped control character inside a string, same two cases
+};
+// rel = parity of the unescaped quotes of the earlier lanes of the warp; p_in = previous byte is a non-quote scalar
+SJ_HD LaneDual lane_structurals_dual(const LaneMasks &m, const LaneQuotes &q, uint32_t rel, uint32_t p_in) {
+    const uint64_t in0 = q.ps ^ (0 - (uint64_t)(rel & 1));   // in_string if the warp starts outside a string
     const uint64_t scalar = ~(m.op | m.ws);
-    const uint64_t nqs = scalar & ~m.quote;
-    const uint64_t follows = (nqs << 1) | (p_in & 1);
-    const uint64_t string_tail = in_string ^ m.quote;
-    LaneOut o;
-    o.structural = (m.op | (scalar & ~follows)) & ~string_tail;
-    o.unescaped_err = (m.ctl & in_string) != 0;
-    return o;
+    const uint64_t follows = (q.nqs << 1) | (p_in & 1);
+    const uint64_t pot = m.op | (scalar & ~follows);         // json_scanner.mojo:24-49
+    const uint64_t tail0 = in0 ^ q.quote;                     // string_tail, json_string_scanner.mojo:41-44
+    LaneDual d;
+    d.m0 = pot & ~tail0;
+    d.m1 = pot & tail0;                                       // in_string complemented => string_tail complemented
+    d.u0 = (m.ctl & in0) != 0;
+    d.u1 = (m.ctl & ~in0) != 0;
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp summary from ballots (all under "warp e_in = 0"):
-//   A, O as above; PB = ballot(lane quote parity); NQ = ballot(bit 63 of non-quote scalar);
-//   FQ = ballot(flipq != 0); FQ63 = ballot(bit 63 of flipq)
+// Tile descriptors for the single-pass look-back (one 64-bit word per tile, generation tagged).
+//   AGG    : what the tile contributes, for both values of "the tile starts inside a string"
+//   PREFIX : the state after the tile and the number of indexes produced up to and including it
 // ------------------------------------------------------------------------------------------------
-SJ_HD SpanFn warp_span(uint32_t A, uint32_t O, uint32_t PB, uint32_t NQ, uint32_t FQ, uint32_t FQ63) {
-    bool lead;
-    const uint32_t e_tail = warp_lane_e_in(A, O, 32, &lead);  // lead == whole warp is backslashes
-    const uint32_t pw = (uint32_t)popc32(PB) & 1u;
-    const uint32_t fw = FQ != 0;
-    const uint32_t po0 = NQ >> 31;
-    const uint32_t po1 = po0 ^ (FQ63 >> 31);
-    return span_make(lead ? 0 : e_tail, pw, po0, lead ? 1 : e_tail, pw ^ fw, po1);
+static const uint32_t DESC_AGG = 1, DESC_PREFIX = 2;
+static const uint32_t EF_UNESCAPED = 1, EF_UTF8 = 2;
+static const uint32_t GEN_MASK = 0xFFFFFu;  // 20-bit generation
+
+struct TileAgg {
+    uint32_t par;        // parity of the tile's unescaped quotes
+    uint32_t e_out, p_out;
+    uint32_t un[2];      // unescaped control character inside a string, if the tile starts outside / inside a string
+    uint32_t u8;         // UTF-8 violation
+    uint32_t c[2];       // structural count, same two cases (<= 2^17)
+};
+struct TilePrefix {
+    uint32_t s_out, e_out, p_out;
+    uint32_t err;        // EF_* accumulated over all tiles so far
+    uint32_t count;      // indexes produced so far
+};
+SJ_HD uint64_t desc_pack_agg(uint32_t gen, const TileAgg &a) {
+    const uint64_t hi = ((uint64_t)(gen & GEN_MASK) << 8) | (DESC_AGG << 6) | ((a.par & 1) << 5) | ((a.e_out & 1) << 4) |
+                        ((a.p_out & 1) << 3) | ((a.un[0] & 1) << 2) | ((a.un[1] & 1) << 1) | (a.u8 & 1);
+    return (hi << 36) | ((uint64_t)(a.c[1] & 0x3FFFFu) << 18) | (uint64_t)(a.c[0] & 0x3FFFFu);
+}
+SJ_HD uint64_t desc_pack_prefix(uint32_t gen, const TilePrefix &p) {
+    const uint64_t hi = ((uint64_t)(gen & GEN_MASK) << 8) | (DESC_PREFIX << 6) | ((p.s_out & 1) << 5) | ((p.e_out & 1) << 4) |
+                        ((p.p_out & 1) << 3) | ((p.err & 3) << 1);
+    return (hi << 36) | (uint64_t)p.count;  // bits [35:32] unused
+}
+SJ_HD uint32_t desc_gen(uint64_t d) { return (uint32_t)(d >> 44) & GEN_MASK; }
+SJ_HD uint32_t desc_status(uint64_t d) { return (uint32_t)(d >> 42) & 3u; }
+SJ_HD TileAgg desc_unpack_agg(uint64_t d) {
+    TileAgg a;
+    const uint32_t f = (uint32_t)(d >> 36);
+    a.par = (f >> 5) & 1;
+    a.e_out = (f >> 4) & 1;
+    a.p_out = (f >> 3) & 1;
+    a.un[0] = (f >> 2) & 1;
+    a.un[1] = (f >> 1) & 1;
+    a.u8 = f & 1;
+    a.c[0] = (uint32_t)d & 0x3FFFFu;
+    a.c[1] = (uint32_t)(d >> 18) & 0x3FFFFu;
+    return a;
+}
+SJ_HD TilePrefix desc_unpack_prefix(uint64_t d) {
+    TilePrefix p;
+    const uint32_t f = (uint32_t)(d >> 36);
+    p.s_out = (f >> 5) & 1;
+    p.e_out = (f >> 4) & 1;
+    p.p_out = (f >> 3) & 1;
+    p.err = (f >> 1) & 3;
+    p.count = (uint32_t)d;  // low 32 bits; the 4 bits [35:32] are unused
+    return p;
+}
+
+// A run of tiles seen as a function of "starts inside a string" (s): parity, counts and error flags.
+struct SpanAcc {
+    uint32_t par, c[2], un[2], u8;
+};
+SJ_HD SpanAcc span_empty() {
+    SpanAcc a = {0, {0, 0}, {0, 0}, 0};
+    return a;
+}
+// older happens first, then newer
+SJ_HD SpanAcc span_concat(const SpanAcc &older, const SpanAcc &newer) {
+    SpanAcc r;
+    r.par = older.par ^ newer.par;
+    const bool flip = (older.par & 1u) != 0;  // no dynamic indexing: these live in registers
+    r.c[0] = older.c[0] + (flip ? newer.c[1] : newer.c[0]);
+    r.c[1] = older.c[1] + (flip ? newer.c[0] : newer.c[1]);
+    r.un[0] = older.un[0] | (flip ? newer.un[1] : newer.un[0]);
+    r.un[1] = older.un[1] | (flip ? newer.un[0] : newer.un[1]);
+    r.u8 = older.u8 | newer.u8;
+    return r;
 }
 
 }  // namespace sjb200

@@ -4,17 +4,18 @@
 //
 // Work decomposition
 //   lane  : 64 consecutive bytes (one 64-bit word of every mask)
-//   warp  : 2 KiB, carries between lanes resolved with ballots (no shuffles of data)
+//   warp  : 2 KiB; carries between lanes resolved with ballots
 //   CTA   : WARPS x 2 KiB = one tile, loaded by ONE bulk async copy (cp.async.bulk -> UBLKCP) into shared
 //           memory behind an mbarrier; the same shared memory is reused to stage the tile's indexes so the
 //           global index write is coalesced 16-byte stores
 //   grid  : one CTA per tile, tile ids handed out by an atomic ticket so that a tile only ever waits for
 //           tiles that are already running (forward progress of the look-back)
-// Cross-tile dependencies, both resolved by single-pass decoupled look-back over 8-byte descriptors that
-// carry a per-call generation number (no reset pass between calls):
-//   1. the (escaped, in-string, previous-scalar) carry: descriptors hold a SpanFn (stage1_core.cuh),
-//      combined by function composition;
-//   2. the output cursor + error flags: descriptors hold (count, flags), combined by (+, |).
+// Carries (stage1_core.cuh): "escaped" and "previous scalar" are resolved locally from the bytes just before a
+// warp / tile (they sit in shared memory; the tile brings a 16-byte halo).  The in-string parity is the only
+// global carry: every lane produces its structural bits for BOTH values of it, every tile publishes
+// {quote parity, count if it starts outside a string, count if inside, error flags for both} in one 8-byte,
+// generation-tagged descriptor, and ONE decoupled look-back yields both the parity entering the tile and the
+// output cursor.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,7 +43,7 @@ struct Stage1Result {       // written by the last tile (mapped pinned host memo
     uint32_t n_valid;       // 0 on UNCLOSED_STRING / UNESCAPED_CHARS / CAPACITY: the reference leaves n untouched
     uint32_t n_written;     // entries produced by the indexer (clipped to capacity in memory)
     int32_t utf8_error;     // 1 iff the input is not valid UTF-8 (always reported when validation is compiled in)
-    uint32_t final_state;   // packed carry after the last byte (bit1 = still inside a string)
+    uint32_t final_state;   // bit1 = still inside a string after the last byte
     uint32_t reserved[2];
 };
 
@@ -53,12 +54,11 @@ struct Stage1Params {
     uint32_t len;           // input length (< 2^32, reference base.mojo:2)
     uint32_t *out;          // device index array
     uint64_t cap;           // its capacity in entries
-    uint64_t *desc1;        // per-tile carry descriptors
-    uint64_t *desc2;        // per-tile count descriptors
+    uint64_t *desc;         // per-tile look-back descriptors
     uint32_t *ticket;       // tile ticket counter, 0 at launch, reset by the last tile
     Stage1Result *result;
     int32_t *dev_status;    // optional device copy of {error, n} for on-device consumers (NCCL), may be null
-    uint32_t gen;           // generation of this call (never 0)
+    uint32_t gen;           // generation of this call (1 .. 2^20-1)
     uint32_t ntiles;
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
 };
@@ -106,14 +106,14 @@ __device__ __forceinline__ uint64_t ld_desc(const uint64_t *p) {
 __device__ __forceinline__ void st_desc(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-// descriptor encodings
-static constexpr uint32_t ST_AGG = 1, ST_PREFIX = 2;
-__device__ __forceinline__ uint64_t d1_make(uint32_t gen, uint32_t status, uint32_t fn) {
-    return ((uint64_t)gen << 32) | (status << 7) | (fn & 0x7F);
-}
-__device__ __forceinline__ uint64_t d2_make(uint32_t gen, uint32_t status, uint32_t err, uint32_t count) {
-    return ((uint64_t)(gen & 0x0FFFFFFFu) << 36) | ((uint64_t)status << 34) | ((uint64_t)(err & 3) << 32) | count;
+// spin until tile j has published something for this generation
+__device__ __forceinline__ uint64_t wait_desc(const uint64_t *desc, int j, uint32_t gen) {
+    uint64_t d = ld_desc(desc + j);
+    while (desc_gen(d) != (gen & GEN_MASK)) {
+        __nanosleep(20);
+        d = ld_desc(desc + j);
+    }
+    return d;
 }
 
 __device__ __forceinline__ uint32_t mask_word(uint32_t w, int64_t g, int64_t vbeg, int64_t vend) {
@@ -126,69 +126,100 @@ __device__ __forceinline__ uint32_t mask_word(uint32_t w, int64_t g, int64_t vbe
     return (w & m) | (0x20202020u & ~m);
 }
 
-static constexpr uint32_t EF_UNESCAPED = 1, EF_UTF8 = 2;
-
 // ---------------------------------------------------------------------------------------------
-// look-backs (executed by warp 0 of a tile)
+// local carry resolution: (e, p) entering the tile / a warp, from the bytes before it
 // ---------------------------------------------------------------------------------------------
-// returns the carry state entering `tile` (tile > 0)
-__device__ __forceinline__ CarryState lookback_carry(const uint64_t *desc1, uint32_t gen, int tile, int lane) {
-    SpanFn acc = SPAN_IDENT;
-    int base = tile - 1;
-    while (true) {
-        const int j = base - lane;
-        uint32_t st = ST_PREFIX, fn = span_const(0, 0, 0);
-        if (j >= 0) {
-            uint64_t d;
-            do {
-                d = ld_desc(desc1 + j);
-            } while ((uint32_t)(d >> 32) != gen);
-            st = ((uint32_t)d >> 7) & 3u;
-            fn = (uint32_t)d & 0x7Fu;
-        }
-        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == ST_PREFIX);
-        const int k = pm ? (__ffs((int)pm) - 1) : 31;  // nearest tile whose inclusive state is known
-        SpanFn f = lane <= k ? fn : SPAN_IDENT;
-        // ordered reduction: lane k is the oldest span, lane 0 the newest
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const SpanFn older = __shfl_down_sync(0xFFFFFFFFu, f, d);
-            if (lane + d < 32) f = span_compose(older, f);
-        }
-        const SpanFn window = __shfl_sync(0xFFFFFFFFu, f, 0);
-        acc = span_compose(window, acc);
-        if (pm) break;
-        base -= 32;
+// tile level: 16 halo bytes at smem_tile[-16..-1]; if they do not decide, the predecessor's descriptor does
+__device__ __forceinline__ PrevState tile_prev_state(const uint8_t *smem_tile, int tile, int lane, const uint64_t *desc,
+                                                     uint32_t gen) {
+    PrevState st = {0, 0, 0};
+    if (tile == 0) return st;  // nothing before the document
+    const uint32_t c = lane < 16 ? (uint32_t)smem_tile[-1 - lane] : 0x20u;
+    const uint32_t bsm = __ballot_sync(0xFFFFFFFFu, c == 0x5Cu);
+    const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, c, 0);
+    st = prev_state(bsm, 16, c1);
+    if (st.unresolved) {  // a backslash run fills the halo: the previous tile knows (it resolved its own carries first)
+        const uint64_t d = wait_desc(desc, tile - 1, gen);
+        const uint32_t f = (uint32_t)(d >> 36);  // e_out / p_out sit at the same bits in both descriptor kinds
+        if (st.unresolved & 1u) st.e = (f >> 4) & 1u;
+        if (st.unresolved & 2u) st.p = (f >> 3) & 1u;
+        st.unresolved = 0;
     }
-    CarryState zero = {0, 0, 0};
-    return span_apply(acc, zero);  // acc starts with a constant function: the argument is irrelevant
+    return st;
 }
 
-// returns the number of indexes produced by all tiles before `tile` (tile > 0) and their OR-ed error flags
-__device__ __forceinline__ void lookback_count(const uint64_t *desc2, uint32_t gen, int tile, int lane, uint32_t &sum,
-                                               uint32_t &err) {
-    const uint64_t want = (uint64_t)(gen & 0x0FFFFFFFu);
-    sum = 0;
-    err = 0;
+// warp level (warp > 0): 32 bytes before the warp's first byte, all inside this tile
+__device__ __forceinline__ PrevState warp_prev_state(const uint8_t *smem_tile, int woff, int lane, int64_t tb, int64_t vbeg,
+                                                     int64_t vend, bool edge, int tile, const uint64_t *desc, uint32_t gen) {
+    uint32_t c = (uint32_t)smem_tile[woff - 1 - lane];
+    if (edge) {
+        const int64_t g = tb + woff - 1 - lane;
+        if (g < vbeg || g >= vend) c = 0x20u;  // outside the document: reads as the reference's 0x20 padding
+    }
+    const uint32_t bsm = __ballot_sync(0xFFFFFFFFu, c == 0x5Cu);
+    const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, c, 0);
+    PrevState st = prev_state(bsm, 32, c1);
+    if (st.unresolved) {  // rare: a backslash run of 31+ bytes ends at the warp boundary; walk it inside the tile
+        const PrevState t = tile_prev_state(smem_tile, tile, lane, desc, gen);
+        // bytes of this tile that may be read before the warp (tile 0: not before the document start)
+        const uint32_t room = (uint32_t)woff - (tile == 0 ? (uint32_t)vbeg : 0u);
+        if (st.unresolved & 1u) {
+            const uint32_t r = backslash_run_before(smem_tile + woff, room);
+            st.e = r < room ? (r & 1u) : escaped_after_run(room, t.e);
+        }
+        if (st.unresolved & 2u) {  // byte -1 is a quote: is it escaped?
+            const uint32_t r = backslash_run_before(smem_tile + woff - 1, room - 1);
+            st.p = r < room - 1 ? (r & 1u) : escaped_after_run(room - 1, t.e);
+        }
+        st.unresolved = 0;
+    }
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// look-back (executed by warp 0 of a tile > 0): parity entering the tile, indexes before it, errors so far
+// ---------------------------------------------------------------------------------------------
+struct LookbackResult {
+    uint32_t s_in, base, err;
+};
+__device__ __forceinline__ LookbackResult lookback(const uint64_t *desc, uint32_t gen, int tile, int lane) {
+    SpanAcc acc = span_empty();  // the already visited (newer) tiles as a function of the parity entering them
     int base = tile - 1;
     while (true) {
         const int j = base - lane;
-        uint32_t st = ST_PREFIX, cnt = 0, er = 0;
+        uint64_t d = 0;
+        uint32_t st = DESC_PREFIX;  // before the first tile: outside a string, nothing produced
         if (j >= 0) {
-            uint64_t d;
-            do {
-                d = ld_desc(desc2 + j);
-            } while ((d >> 36) != want);
-            st = (uint32_t)(d >> 34) & 3u;
-            er = (uint32_t)(d >> 32) & 3u;
-            cnt = (uint32_t)d;
+            d = wait_desc(desc, j, gen);
+            st = desc_status(d);
         }
-        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == ST_PREFIX);
-        const int k = pm ? (__ffs((int)pm) - 1) : 31;
-        const bool take = lane <= k;
-        sum += __reduce_add_sync(0xFFFFFFFFu, take ? cnt : 0u);
-        err |= __reduce_or_sync(0xFFFFFFFFu, take ? er : 0u);
-        if (pm) break;
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == DESC_PREFIX);
+        const int k = pm ? (__ffs((int)pm) - 1) : 32;  // nearest tile whose inclusive state is known
+        const bool isagg = lane < k;
+        const TileAgg a = desc_unpack_agg(d);
+        // parity of the AGG tiles older than this lane's tile inside the window (higher lanes are older)
+        const uint32_t pbm = __ballot_sync(0xFFFFFFFFu, isagg && a.par);
+        const uint32_t rel = (uint32_t)__popc(pbm & ~((2u << lane) - 1u)) & 1u;
+        SpanAcc win;
+        win.par = (uint32_t)__popc(pbm) & 1u;
+        win.c[0] = __reduce_add_sync(0xFFFFFFFFu, isagg ? (rel ? a.c[1] : a.c[0]) : 0u);
+        win.c[1] = __reduce_add_sync(0xFFFFFFFFu, isagg ? (rel ? a.c[0] : a.c[1]) : 0u);
+        const uint32_t unx = rel ? a.un[1] : a.un[0], uny = rel ? a.un[0] : a.un[1];
+        const uint32_t eall = __reduce_or_sync(0xFFFFFFFFu, isagg ? (unx | (uny << 1) | (a.u8 << 2)) : 0u);
+        win.un[0] = eall & 1u;
+        win.un[1] = (eall >> 1) & 1u;
+        win.u8 = (eall >> 2) & 1u;
+        acc = span_concat(win, acc);
+        if (pm) {
+            const uint64_t dk = __shfl_sync(0xFFFFFFFFu, d, k);
+            TilePrefix p = {0, 0, 0, 0, 0};              // state before the first tile
+            if (base - k >= 0) p = desc_unpack_prefix(dk);
+            LookbackResult r;
+            r.s_in = p.s_out ^ acc.par;
+            r.base = p.count + (p.s_out ? acc.c[1] : acc.c[0]);
+            r.err = p.err | ((p.s_out ? acc.un[1] : acc.un[0]) ? EF_UNESCAPED : 0u) | (acc.u8 ? EF_UTF8 : 0u);
+            return r;
+        }
         base -= 32;
     }
 }
@@ -200,22 +231,27 @@ template <int WARPS>
 struct TileCfg {
     static constexpr int THREADS = WARPS * 32;
     static constexpr int TILE = WARPS * 2048;                 // bytes per tile
-    static constexpr int STAGE_CAP = TILE / 2;                // indexes staged in shared memory (density <= 0.5)
+    // indexes staged in shared memory: up to 0.5 per byte for the small tiles, 0.25 for the big ones (denser tiles
+    // write straight to global memory); the staging area overlays the dead input tile
+    static constexpr int STAGE_CAP = WARPS >= 16 ? TILE / 4 : TILE / 2;
     static constexpr int SMEM_BYTES = (STAGE_CAP + 4) * 4;    // >= 16 + TILE
     static_assert(SMEM_BYTES >= 16 + TILE, "staging must cover the input tile");
+    // resident CTAs per SM we ask the register allocator to allow (2048 threads / 64 K registers per SM)
+    static constexpr int MIN_CTAS = WARPS <= 4 ? 8 : (WARPS == 8 ? 4 : (WARPS == 16 ? 2 : 1));
 };
 
 template <int WARPS, bool UTF8>
-__global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P) {
+__global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_kernel(const Stage1Params P) {
     using Cfg = TileCfg<WARPS>;
     constexpr int TILE = Cfg::TILE;
     extern __shared__ __align__(128) uint8_t smem_raw[];   // [0,16) halo, [16,16+TILE) tile; later: index staging
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_span[WARPS];        // SpanFn of each warp
-    __shared__ uint32_t s_span_before[WARPS]; // composition of the warps before it
-    __shared__ uint32_t s_carry_in;           // packed CarryState entering the tile
-    __shared__ uint32_t s_wcnt[WARPS], s_werr[WARPS], s_woff[WARPS];
+    __shared__ uint32_t s_wc0[WARPS], s_wc1[WARPS];   // warp counts if the warp starts outside / inside a string
+    __shared__ uint32_t s_wflags[WARPS];              // bit0 quote parity, bit1/2 unescaped-control (outside/inside), bit3 utf8
+    __shared__ uint32_t s_woff[WARPS];                // rank of the warp's first index inside the tile (actual parity)
+    __shared__ uint32_t s_ws[WARPS];                  // actual "starts inside a string" of each warp
+    __shared__ uint32_t s_tail;                       // bit0 e_out, bit1 p_out of the tile
     __shared__ uint32_t s_total, s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,18 +271,21 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
         int64_t nbytes = alen - tb;
         nbytes = nbytes > TILE ? TILE : nbytes;
         nbytes = (nbytes + 15) & ~15ll;                     // stays inside the last 16-byte line of the data
-        const uint32_t halo = tile > 0 ? 16u : 0u;          // 16 bytes of the previous tile (UTF-8 look-behind)
+        const uint32_t halo = tile > 0 ? 16u : 0u;          // 16 bytes of the previous tile (carry look-behind)
         mbar_expect_tx(bar, (uint32_t)nbytes + halo);
         bulk_load(smem_u32(smem_raw) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar);
     }
     mbar_wait(bar, 0);
+    const uint8_t *smem_tile = smem_raw + 16;
 
-    // ---- phase 1: this lane's 64 bytes -> masks ---------------------------------------------------
-    const int off = warp * 2048 + lane * 64;
+    // ---- this lane's 64 bytes -> masks ---------------------------------------------------------------
+    const int woff = warp * 2048;
+    const int off = woff + lane * 64;
     const int64_t g0 = tb + off;
+    const bool edge = (tile == 0) || (tb + TILE > alen);
     uint32_t w[16];
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(smem_raw + 16 + off);
+        const uint4 *src = reinterpret_cast<const uint4 *>(smem_tile + off);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint4 v = src[q];
@@ -256,13 +295,15 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
             w[4 * q + 3] = v.w;
         }
     }
-    uint32_t prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_raw + 16 + off - 4) : 0u;
-    const bool edge = (tile == 0) || (tb + TILE > alen);
+    uint32_t prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_tile + off - 4) : 0u;
     if (edge) {  // only the first and last tile: bytes outside [mis, alen) read as 0x20 (reference tail padding)
 #pragma unroll
         for (int k = 0; k < 16; k++) w[k] = mask_word(w[k], g0 + 4 * k, (int64_t)P.mis, alen);
         if (UTF8) prev = (g0 == 0) ? 0x20202020u : mask_word(prev, g0 - 4, (int64_t)P.mis, alen);
     }
+    // carries entering the warp, from the bytes before it (warp 0: the halo / the previous tile)
+    const PrevState wst = warp == 0 ? tile_prev_state(smem_tile, tile, lane, P.desc, P.gen)
+                                    : warp_prev_state(smem_tile, woff, lane, tb, (int64_t)P.mis, alen, edge, tile, P.desc, P.gen);
 
     LaneMasks m;
     uint32_t u8err = 0;
@@ -290,117 +331,94 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
             }
         }
     }
-    // in-warp escape resolution (assuming the warp itself starts unescaped)
+    // escapes and quotes, exact; structural bits for both in-string parities
     const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
     const uint32_t bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
-    {
-        bool lead;
-        const uint32_t e_in = warp_lane_e_in(bA, bO, lane, &lead);
-        lane_resolve_quotes(m, e_in, lead);
-    }
-    uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (m.ps >> 63) != 0);
-    uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (lane_nonquote_scalar(m) >> 63) != 0);
-    {
-        const uint32_t bFQ = __ballot_sync(0xFFFFFFFFu, m.flipq != 0);
-        const uint32_t bFQ63 = __ballot_sync(0xFFFFFFFFu, (m.flipq >> 63) != 0);
-        if (lane == 0) s_span[warp] = warp_span(bA, bO, bPB, bNQ, bFQ, bFQ63);
-    }
-    __syncthreads();  // A: warp spans visible; every lane has its bytes in registers (shared input is dead)
-
-    // ---- carry look-back (warp 0) -------------------------------------------------------------------
-    if (warp == 0) {
-        SpanFn f = lane < WARPS ? s_span[lane] : SPAN_IDENT;
-#pragma unroll
-        for (int d = 1; d < WARPS; d <<= 1) {
-            const SpanFn older = __shfl_up_sync(0xFFFFFFFFu, f, d);
-            if (lane >= d) f = span_compose(older, f);
-        }
-        SpanFn before = __shfl_up_sync(0xFFFFFFFFu, f, 1);
-        if (lane == 0) before = SPAN_IDENT;
-        if (lane < WARPS) s_span_before[lane] = before;
-        const SpanFn tile_fn = __shfl_sync(0xFFFFFFFFu, f, WARPS - 1);
-        CarryState cin = {0, 0, 0};
-        if (tile > 0) {
-            if (lane == 0) st_desc(P.desc1 + tile, d1_make(P.gen, ST_AGG, tile_fn));
-            cin = lookback_carry(P.desc1, P.gen, tile, lane);
-        }
-        const CarryState cout = span_apply(tile_fn, cin);
-        if (lane == 0) {
-            st_desc(P.desc1 + tile, d1_make(P.gen, ST_PREFIX, span_const(cout.e, cout.s, cout.p)));
-            s_carry_in = carry_pack(cin) | (carry_pack(cout) << 8);
-        }
-    }
-    __syncthreads();  // B: carry entering the tile known
-
-    // ---- phase 2: exact carries -> structurals -> counts -------------------------------------------
-    const CarryState tile_in = carry_unpack(s_carry_in);
-    const CarryState cw = span_apply(s_span_before[warp], tile_in);
-    if (cw.e) {  // rare: the warp's first byte is escaped by the previous warp/tile
-        lane_apply_escape_carry(m);
-        bPB = __ballot_sync(0xFFFFFFFFu, (m.ps >> 63) != 0);
-        bNQ = __ballot_sync(0xFFFFFFFFu, (lane_nonquote_scalar(m) >> 63) != 0);
-    }
+    const LaneQuotes q = lane_quotes(m, warp_lane_e_in(bA, bO, lane, wst.e));
+    const uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (q.ps >> 63) != 0);
+    const uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (q.nqs >> 63) != 0);
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t s_in = cw.s ^ ((uint32_t)__popc(bPB & lt) & 1u);
-    const uint32_t p_in = lane ? ((bNQ >> (lane - 1)) & 1u) : cw.p;
-    const LaneOut lo = lane_structurals(m, s_in, p_in);
-    const uint32_t st_lo = (uint32_t)lo.structural, st_hi = (uint32_t)(lo.structural >> 32);
-    const uint32_t cnt = (uint32_t)(__popc(st_lo) + __popc(st_hi));
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const uint32_t excl = incl - cnt;
+    const uint32_t rel = (uint32_t)__popc(bPB & lt) & 1u;
+    const uint32_t p_in = lane ? ((bNQ >> (lane - 1)) & 1u) : wst.p;
+    const LaneDual dual = lane_structurals_dual(m, q, rel, p_in);
+    const uint32_t c0 = (uint32_t)__popcll(dual.m0), c1 = (uint32_t)__popcll(dual.m1);
     {
-        const uint32_t e1 = __ballot_sync(0xFFFFFFFFu, lo.unescaped_err != 0);
-        const uint32_t e2 = __ballot_sync(0xFFFFFFFFu, u8err != 0);
-        if (lane == 31) {
-            s_wcnt[warp] = incl;
-            s_werr[warp] = (e1 ? EF_UNESCAPED : 0u) | (e2 ? EF_UTF8 : 0u);
+        const uint32_t wc0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+        const uint32_t wc1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+        const uint32_t fl = __reduce_or_sync(0xFFFFFFFFu, (dual.u0 << 1) | (dual.u1 << 2) | (u8err << 3));
+        if (lane == 0) {
+            s_wc0[warp] = wc0;
+            s_wc1[warp] = wc1;
+            s_wflags[warp] = fl | ((uint32_t)__popc(bPB) & 1u);
+            if (warp == WARPS - 1) s_tail = warp_lane_e_in(bA, bO, 32, wst.e) | ((bNQ >> 31) << 1);
         }
     }
-    __syncthreads();  // C
+    __syncthreads();  // A: warp summaries visible; every lane has its bytes in registers (shared input is dead)
 
-    // ---- count look-back (warp 0), verdict (last tile) ------------------------------------------------
+    // ---- warp 0: tile aggregate, look-back, inclusive prefix, verdict --------------------------------
     if (warp == 0) {
-        const uint32_t c = lane < WARPS ? s_wcnt[lane] : 0u;
-        const uint32_t e = lane < WARPS ? s_werr[lane] : 0u;
-        uint32_t ci = c;
+        const bool have = lane < WARPS;
+        const uint32_t fl = have ? s_wflags[lane] : 0u;
+        const uint32_t parb = __ballot_sync(0xFFFFFFFFu, fl & 1u);
+        const uint32_t R = (uint32_t)__popc(parb & lt) & 1u;  // parity of the warps before this one
+        const uint32_t a0 = have ? s_wc0[lane] : 0u, a1 = have ? s_wc1[lane] : 0u;
+        const uint32_t t0 = R ? a1 : a0, t1 = R ? a0 : a1;    // this warp's count if the TILE starts outside / inside
+        uint32_t i0 = t0, i1 = t1;
 #pragma unroll
         for (int d = 1; d < WARPS; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ci, d);
-            if (lane >= d) ci += t;
+            const uint32_t x0 = __shfl_up_sync(0xFFFFFFFFu, i0, d);
+            const uint32_t x1 = __shfl_up_sync(0xFFFFFFFFu, i1, d);
+            if (lane >= d) {
+                i0 += x0;
+                i1 += x1;
+            }
         }
-        if (lane < WARPS) s_woff[lane] = ci - c;
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, ci, WARPS - 1);
-        uint32_t err = __reduce_or_sync(0xFFFFFFFFu, e);
-        uint32_t base = 0;
+        TileAgg agg;
+        agg.par = (uint32_t)__popc(parb) & 1u;
+        agg.c[0] = __shfl_sync(0xFFFFFFFFu, i0, WARPS - 1);
+        agg.c[1] = __shfl_sync(0xFFFFFFFFu, i1, WARPS - 1);
+        const uint32_t un0 = (fl >> (R ? 2 : 1)) & 1u, un1 = (fl >> (R ? 1 : 2)) & 1u;
+        const uint32_t eall = __reduce_or_sync(0xFFFFFFFFu, un0 | (un1 << 1) | (((fl >> 3) & 1u) << 2));
+        agg.un[0] = eall & 1u;
+        agg.un[1] = (eall >> 1) & 1u;
+        agg.u8 = (eall >> 2) & 1u;
+        const uint32_t tail = s_tail;
+        agg.e_out = tail & 1u;
+        agg.p_out = (tail >> 1) & 1u;
+        LookbackResult lb = {0, 0, 0};
         if (tile > 0) {
-            if (lane == 0) st_desc(P.desc2 + tile, d2_make(P.gen, ST_AGG, err, total));
-            uint32_t perr;
-            lookback_count(P.desc2, P.gen, tile, lane, base, perr);
-            err |= perr;
+            if (lane == 0) st_desc(P.desc + tile, desc_pack_agg(P.gen, agg));
+            lb = lookback(P.desc, P.gen, tile, lane);
+        }
+        const uint32_t s_in = lb.s_in & 1u;
+        const uint32_t total = s_in ? agg.c[1] : agg.c[0];
+        TilePrefix pre;
+        pre.s_out = s_in ^ agg.par;
+        pre.e_out = agg.e_out;
+        pre.p_out = agg.p_out;
+        pre.err = lb.err | ((s_in ? agg.un[1] : agg.un[0]) ? EF_UNESCAPED : 0u) | (agg.u8 ? EF_UTF8 : 0u);
+        pre.count = lb.base + total;
+        if (lane == 0) st_desc(P.desc + tile, desc_pack_prefix(P.gen, pre));
+        if (have) {
+            s_woff[lane] = s_in ? i1 - t1 : i0 - t0;
+            s_ws[lane] = s_in ^ R;
         }
         if (lane == 0) {
-            st_desc(P.desc2 + tile, d2_make(P.gen, ST_PREFIX, err, base + total));
             s_total = total;
-            s_base = base;
+            s_base = lb.base;
             if (tile == (int)P.ntiles - 1) {
                 // finish(): reference json_structural_indexer.mojo:147-186, same priority order
-                const CarryState cout = carry_unpack(s_carry_in >> 8);
-                const uint64_t n = (uint64_t)base + total;
+                const uint64_t n = (uint64_t)lb.base + total;
                 Stage1Result r;
                 r.n = (uint32_t)n;
                 r.n_written = (uint32_t)n;
                 r.n_valid = 0;
-                r.utf8_error = (err & EF_UTF8) ? 1 : 0;
-                r.final_state = carry_pack(cout);
+                r.utf8_error = (pre.err & EF_UTF8) ? 1 : 0;
+                r.final_state = pre.s_out << 1;
                 r.reserved[0] = r.reserved[1] = 0;
-                if (cout.s) {
+                if (pre.s_out) {
                     r.error = ERR_UNCLOSED_STRING;
-                } else if (err & EF_UNESCAPED) {
+                } else if (pre.err & EF_UNESCAPED) {
                     r.error = ERR_UNESCAPED_CHARS;
                 } else if (n + 3 > P.cap) {
                     r.error = ERR_CAPACITY;
@@ -410,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
                     P.out[n + 1] = P.len;
                     P.out[n + 2] = 0;
                     if (n == 0) r.error = ERR_EMPTY;
-                    else if ((P.flags & 1u) && (err & EF_UTF8)) r.error = ERR_UTF8_ERROR;
+                    else if ((P.flags & 1u) && (pre.err & EF_UTF8)) r.error = ERR_UTF8_ERROR;
                     else r.error = ERR_SUCCESS;
                 }
                 *P.result = r;
@@ -422,40 +440,51 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
             }
         }
     }
-    __syncthreads();  // D
+    __syncthreads();  // B: parity entering every warp and the output cursor are known
 
     // ---- flatten: bitmask -> ascending uint32 indexes (BitIndexer.write, :46-58) -----------------------
+    const uint32_t s_lane = s_ws[warp] & 1u;   // the WARP starts inside a string? (the lane's own offset is already in m0/m1)
+    const uint64_t structural = s_lane ? dual.m1 : dual.m0;
+    const uint32_t cnt = s_lane ? c1 : c0;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
     const uint32_t total = s_total, base = s_base;
-    const uint32_t my = s_woff[warp] + excl;             // rank of this lane's first index inside the tile
-    const uint32_t v0 = (uint32_t)(g0 - (int64_t)P.mis); // index value of bit 0 of the chunk
+    const uint32_t my = s_woff[warp] + incl - cnt;           // rank of this lane's first index inside the tile
+    const uint32_t v0 = (uint32_t)(g0 - (int64_t)P.mis);     // index value of bit 0 of the chunk
+    // bit-reversed words: clz finds the lowest structural, one FLO per index
+    uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
     if (total <= (uint32_t)Cfg::STAGE_CAP) {
         uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
         // keep shared and global 16-byte phases equal (the output pointer itself may be only 4-byte aligned)
         const uint32_t a = (base + (uint32_t)((reinterpret_cast<uintptr_t>(P.out) >> 2) & 3u)) & 3u;
-        uint32_t o = a + my;
-        uint32_t bits = st_lo;
-        while (bits) {
-            stage[o++] = v0 + (uint32_t)(__ffs((int)bits) - 1);
-            bits &= bits - 1;
+        uint32_t *dst = stage + a + my;
+        while (rlo) {
+            const int b = __clz((int)rlo);
+            *dst++ = v0 + (uint32_t)b;
+            rlo &= ~(0x80000000u >> b);
         }
-        bits = st_hi;
-        while (bits) {
-            stage[o++] = v0 + 32u + (uint32_t)(__ffs((int)bits) - 1);
-            bits &= bits - 1;
+        while (rhi) {
+            const int b = __clz((int)rhi);
+            *dst++ = v0 + 32u + (uint32_t)b;
+            rhi &= ~(0x80000000u >> b);
         }
-        __syncthreads();  // E
+        __syncthreads();  // C
         // coalesced copy-out: vector v holds staged entries [4v, 4v+4) = global entries gbase + 4v ..
         const int64_t gbase = (int64_t)base - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
         const uint32_t end = a + total;
         const uint32_t nvec = (end + 3u) >> 2;
         for (uint32_t v = tid; v < nvec; v += Cfg::THREADS) {
-            const uint4 q = reinterpret_cast<const uint4 *>(stage)[v];
+            const uint4 qv = reinterpret_cast<const uint4 *>(stage)[v];
             const uint32_t j = 4u * v;
             const int64_t g = gbase + (int64_t)j;
             if (j >= a && j + 4u <= end && (uint64_t)(g + 4) <= P.cap) {
-                *reinterpret_cast<uint4 *>(P.out + g) = q;
+                *reinterpret_cast<uint4 *>(P.out + g) = qv;
             } else {
-                const uint32_t vals[4] = {q.x, q.y, q.z, q.w};
+                const uint32_t vals[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (j + i >= a && j + i < end && (uint64_t)(g + i) < P.cap) P.out[g + i] = vals[i];
@@ -464,17 +493,17 @@ __global__ void __launch_bounds__(WARPS * 32) stage1_kernel(const Stage1Params P
     } else {
         // very dense tile (> 0.5 structurals per byte): write straight to global memory
         uint64_t o = (uint64_t)base + my;
-        uint32_t bits = st_lo;
-        while (bits) {
-            if (o < P.cap) P.out[o] = v0 + (uint32_t)(__ffs((int)bits) - 1);
+        while (rlo) {
+            const int b = __clz((int)rlo);
+            if (o < P.cap) P.out[o] = v0 + (uint32_t)b;
             o++;
-            bits &= bits - 1;
+            rlo &= ~(0x80000000u >> b);
         }
-        bits = st_hi;
-        while (bits) {
-            if (o < P.cap) P.out[o] = v0 + 32u + (uint32_t)(__ffs((int)bits) - 1);
+        while (rhi) {
+            const int b = __clz((int)rhi);
+            if (o < P.cap) P.out[o] = v0 + 32u + (uint32_t)b;
             o++;
-            bits &= bits - 1;
+            rhi &= ~(0x80000000u >> b);
         }
     }
 }

@@ -44,7 +44,7 @@ class Stage1Context:
     def set_warps(self, warps: int) -> None:
         rc = self._lib.sjb200_ctx_set_warps(self._ctx, warps)
         if rc != errors.SUCCESS:
-            raise ValueError("warps must be 0, 2, 4 or 8")
+            raise ValueError("warps must be 0, 2, 4, 8, 16 or 32")
 
     def close(self):
         if self._ctx:

@@ -24,8 +24,6 @@ def lib():
                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_uint32]
         L.emu_bitplanes32.restype = None
         L.emu_bitplanes32.argtypes = [C.c_void_p, C.c_void_p]
-        L.emu_span_compose.restype = C.c_uint32
-        L.emu_span_compose.argtypes = [C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
 

@@ -2,11 +2,12 @@
 //
 // Host-side lane-by-lane emulation of the CUDA stage-1 kernel's phase structure, built from the very
 // same header (mojo_simdjson_b200/csrc/stage1_core.cuh) the kernel compiles.  It lets the CPU test suite
-// check every bit trick (byte transpose, bit-plane butterfly, plane classifier, bit-sliced UTF-8, escape
-// carry algebra, span composition, edge masking, index arithmetic) against the oracle with no GPU.
-// Warp collectives are emulated by looping over the 32 lanes between phases; the decoupled look-back is
-// emulated by carrying the composed state sequentially from tile to tile.  It is NOT a CPU fallback: the
-// product library never links it.
+// check every bit trick (byte transpose, bit-plane butterfly, plane classifier, bit-sliced UTF-8, local
+// carry resolution, dual-parity structural masks, descriptor packing, look-back window algebra, edge
+// masking, index arithmetic) against the oracle with no GPU.  Warp collectives are emulated by looping over
+// the 32 lanes between phases; the decoupled look-back is emulated over the packed descriptors with a small
+// window and an arbitrary pattern of "which earlier tiles already published their inclusive prefix".
+// It is NOT a CPU fallback: the product library never links it.
 #include <stdint.h>
 #include <string.h>
 #include <vector>
@@ -32,13 +33,105 @@ uint32_t mask_word(uint32_t w, int64_t g, int64_t vbeg, int64_t vend) {
 
 struct Lane {
     LaneMasks m;
-    bool all;
-    uint32_t tpar;
-    uint32_t u8err;
-    uint32_t e_in;
-    bool lead;
-    LaneOut out;
+    LaneQuotes q;
+    LaneDual d;
+    uint32_t u8err, rel, c0, c1;
 };
+
+// mirrors tile_prev_state() of the kernel
+PrevState tile_prev_state(const uint8_t *smem_tile, int64_t tile, const std::vector<uint64_t> &desc) {
+    PrevState st = {0, 0, 0};
+    if (tile == 0) return st;
+    uint32_t bsm = 0;
+    for (int l = 0; l < 16; l++) bsm |= (uint32_t)(smem_tile[-1 - l] == 0x5C) << l;
+    st = prev_state(bsm, 16, smem_tile[-1]);
+    if (st.unresolved) {
+        const uint64_t d = desc[(size_t)tile - 1];
+        const uint32_t f = (uint32_t)(d >> 36);
+        if (st.unresolved & 1u) st.e = (f >> 4) & 1u;
+        if (st.unresolved & 2u) st.p = (f >> 3) & 1u;
+        st.unresolved = 0;
+    }
+    return st;
+}
+
+// mirrors warp_prev_state()
+PrevState warp_prev_state(const uint8_t *smem_tile, int woff, int64_t tb, int64_t vbeg, int64_t vend, bool edge, int64_t tile,
+                          const std::vector<uint64_t> &desc) {
+    uint32_t bsm = 0, c1 = 0;
+    for (int l = 0; l < 32; l++) {
+        uint32_t c = smem_tile[woff - 1 - l];
+        if (edge) {
+            const int64_t g = tb + woff - 1 - l;
+            if (g < vbeg || g >= vend) c = 0x20;
+        }
+        if (l == 0) c1 = c;
+        bsm |= (uint32_t)(c == 0x5C) << l;
+    }
+    PrevState st = prev_state(bsm, 32, c1);
+    if (st.unresolved) {
+        const PrevState t = tile_prev_state(smem_tile, tile, desc);
+        const uint32_t room = (uint32_t)woff - (tile == 0 ? (uint32_t)vbeg : 0u);
+        if (st.unresolved & 1u) {
+            const uint32_t r = backslash_run_before(smem_tile + woff, room);
+            st.e = r < room ? (r & 1u) : escaped_after_run(room, t.e);
+        }
+        if (st.unresolved & 2u) {
+            const uint32_t r = backslash_run_before(smem_tile + woff - 1, room - 1);
+            st.p = r < room - 1 ? (r & 1u) : escaped_after_run(room - 1, t.e);
+        }
+        st.unresolved = 0;
+    }
+    return st;
+}
+
+struct LookbackResult {
+    uint32_t s_in, base, err;
+};
+// mirrors lookback(): `window` lanes instead of 32; visible[j] says which descriptor kind tile j shows
+LookbackResult lookback(const std::vector<uint64_t> &agg, const std::vector<uint64_t> &prefix, const std::vector<char> &shows_prefix,
+                        int64_t tile, int window) {
+    SpanAcc acc = span_empty();
+    int64_t base = tile - 1;
+    for (;;) {
+        // lane l looks at tile base - l
+        int k = window;
+        std::vector<uint64_t> d((size_t)window, 0);
+        for (int l = window - 1; l >= 0; l--) {
+            const int64_t j = base - l;
+            bool is_prefix = true;
+            if (j >= 0) {
+                is_prefix = shows_prefix[(size_t)j] != 0;
+                d[(size_t)l] = is_prefix ? prefix[(size_t)j] : agg[(size_t)j];
+            }
+            if (is_prefix) k = l;  // ends with the lowest such lane = nearest tile
+        }
+        uint32_t pbm = 0;
+        for (int l = 0; l < k; l++) pbm |= (desc_unpack_agg(d[(size_t)l]).par & 1u) << l;
+        SpanAcc win = span_empty();
+        win.par = (uint32_t)popc32(pbm) & 1u;
+        for (int l = 0; l < k; l++) {
+            const TileAgg a = desc_unpack_agg(d[(size_t)l]);
+            const uint32_t rel = (uint32_t)popc32(pbm & ~((2u << l) - 1u)) & 1u;
+            win.c[0] += a.c[rel];
+            win.c[1] += a.c[rel ^ 1u];
+            win.un[0] |= a.un[rel];
+            win.un[1] |= a.un[rel ^ 1u];
+            win.u8 |= a.u8;
+        }
+        acc = span_concat(win, acc);
+        if (k < window) {
+            TilePrefix p = {0, 0, 0, 0, 0};
+            if (base - k >= 0) p = desc_unpack_prefix(d[(size_t)k]);
+            LookbackResult r;
+            r.s_in = p.s_out ^ acc.par;
+            r.base = p.count + acc.c[p.s_out];
+            r.err = p.err | (acc.un[p.s_out] ? EF_UNESCAPED : 0u) | (acc.u8 ? EF_UTF8 : 0u);
+            return r;
+        }
+        base -= window;
+    }
+}
 
 }  // namespace
 
@@ -48,44 +141,47 @@ extern "C" int32_t emu_stage1(const uint8_t *buf, uint64_t len, uint32_t mis, in
     if (utf8_err_out) *utf8_err_out = 0;
     if (len > 0xFFFFFFFFull) return 1;
     if (len == 0) return 13;
+    const uint32_t gen = 0x5A5A5u;
     const int64_t TILE = (int64_t)warps * 2048;
     const int64_t alen = (int64_t)mis + (int64_t)len;
     const int64_t ntiles = (alen + TILE - 1) / TILE;
     // aligned image of memory: hostile bytes wherever the kernel must not look
     std::vector<uint8_t> mem((size_t)(ntiles * TILE + 64), 0);
-    for (size_t i = 0; i < mem.size(); i++) mem[i] = (i & 1) ? 0x22 : 0xF4;
+    for (size_t i = 0; i < mem.size(); i++) mem[i] = (i & 1) ? 0x5C : 0xF4;
     memcpy(mem.data() + mis, buf, (size_t)len);
 
-    CarryState carry = {0, 0, 0};
-    uint64_t total = 0;
-    uint32_t err_unescaped = 0, err_utf8 = 0;
+    std::vector<uint64_t> d_agg((size_t)ntiles), d_prefix((size_t)ntiles), d_either((size_t)ntiles);
+    std::vector<char> shows_prefix((size_t)ntiles);
+    uint64_t total_written = 0;
+    TilePrefix last = {0, 0, 0, 0, 0};
     std::vector<uint8_t> smem((size_t)TILE + 16);
 
     for (int64_t tile = 0; tile < ntiles; tile++) {
         const int64_t tb = tile * TILE;
-        // what the bulk copy leaves in shared memory: 16 halo bytes (tile > 0) + the tile, stale bytes past
-        // the rounded-up end of the data
-        for (size_t i = 0; i < smem.size(); i++) smem[i] = 0xF4;  // stale
+        for (size_t i = 0; i < smem.size(); i++) smem[i] = 0x5C;  // stale shared memory
         int64_t nbytes = alen - tb;
         if (nbytes > TILE) nbytes = TILE;
         nbytes = (nbytes + 15) & ~15ll;
         memcpy(smem.data() + 16, mem.data() + tb, (size_t)nbytes);
         if (tile > 0) memcpy(smem.data(), mem.data() + tb - 16, 16);
+        const uint8_t *smem_tile = smem.data() + 16;
         const bool edge = (tile == 0) || (tb + TILE > alen);
 
         std::vector<Lane> L((size_t)warps * 32);
-        std::vector<SpanFn> wspan((size_t)warps);
-        std::vector<uint32_t> bA(warps), bO(warps), bPB(warps), bNQ(warps);
-        // ---- phase 1: local classification, in-warp escape resolution, warp span ----
+        std::vector<uint32_t> wc0(warps), wc1(warps), wflags(warps);
+        uint32_t tail = 0;
         for (int w = 0; w < warps; w++) {
+            const int woff = w * 2048;
+            const PrevState wst = w == 0 ? tile_prev_state(smem_tile, tile, d_either)
+                                         : warp_prev_state(smem_tile, woff, tb, mis, alen, edge, tile, d_either);
             uint32_t A = 0, O = 0;
             for (int l = 0; l < 32; l++) {
                 Lane &ln = L[(size_t)w * 32 + l];
-                const int64_t off = (int64_t)w * 2048 + (int64_t)l * 64;
+                const int64_t off = woff + (int64_t)l * 64;
                 const int64_t g0 = tb + off;
                 uint32_t words[16], prev;
-                memcpy(words, smem.data() + 16 + off, 64);
-                memcpy(&prev, smem.data() + 16 + off - 4, 4);
+                memcpy(words, smem_tile + off, 64);
+                memcpy(&prev, smem_tile + off - 4, 4);
                 if (edge) {
                     for (int k = 0; k < 16; k++) words[k] = mask_word(words[k], g0 + 4 * k, mis, alen);
                     prev = (g0 == 0) ? 0x20202020u : mask_word(prev, g0 - 4, mis, alen);
@@ -106,85 +202,111 @@ extern "C" int32_t emu_stage1(const uint8_t *buf, uint64_t len, uint32_t mis, in
                 uint32_t tail_must;
                 uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
                 ln.u8err = (ue != 0) || (g0 + 64 == alen && tail_must != 0);
-                ln.all = lane_all_backslash(ln.m.bs);
-                ln.tpar = lane_trailing_run_parity(ln.m.bs);
-                A |= (uint32_t)ln.all << l;
-                O |= ln.tpar << l;
+                A |= (uint32_t)lane_all_backslash(ln.m.bs) << l;
+                O |= lane_trailing_run_parity(ln.m.bs) << l;
             }
-            uint32_t PB = 0, NQ = 0, FQ = 0, FQ63 = 0;
+            uint32_t PB = 0, NQ = 0;
             for (int l = 0; l < 32; l++) {
                 Lane &ln = L[(size_t)w * 32 + l];
-                ln.e_in = warp_lane_e_in(A, O, l, &ln.lead);
-                lane_resolve_quotes(ln.m, ln.e_in, ln.lead);
-                PB |= (uint32_t)(ln.m.ps >> 63) << l;
-                NQ |= (uint32_t)(lane_nonquote_scalar(ln.m) >> 63) << l;
-                FQ |= (uint32_t)(ln.m.flipq != 0) << l;
-                FQ63 |= (uint32_t)(ln.m.flipq >> 63) << l;
+                ln.q = lane_quotes(ln.m, warp_lane_e_in(A, O, l, wst.e));
+                PB |= (uint32_t)(ln.q.ps >> 63) << l;
+                NQ |= (uint32_t)(ln.q.nqs >> 63) << l;
             }
-            bA[w] = A; bO[w] = O; bPB[w] = PB; bNQ[w] = NQ;
-            wspan[w] = warp_span(A, O, PB, NQ, FQ, FQ63);
-        }
-        // ---- tile span, look-back (sequential here) ----
-        std::vector<SpanFn> wprefix((size_t)warps);
-        SpanFn acc = SPAN_IDENT;
-        for (int w = 0; w < warps; w++) {
-            wprefix[w] = acc;
-            acc = span_compose(acc, wspan[w]);
-        }
-        const CarryState tile_in = carry;
-        carry = span_apply(acc, tile_in);
-        // ---- phase 2: exact carries, structurals, counts, extraction ----
-        for (int w = 0; w < warps; w++) {
-            const CarryState cw = span_apply(wprefix[w], tile_in);
-            uint32_t PB = bPB[w], NQ = bNQ[w];
-            if (cw.e) {
-                PB = 0; NQ = 0;
-                for (int l = 0; l < 32; l++) {
-                    Lane &ln = L[(size_t)w * 32 + l];
-                    lane_apply_escape_carry(ln.m);
-                    PB |= (uint32_t)(ln.m.ps >> 63) << l;
-                    NQ |= (uint32_t)(lane_nonquote_scalar(ln.m) >> 63) << l;
-                }
-            }
+            uint32_t fl = 0;
+            wc0[w] = wc1[w] = 0;
             for (int l = 0; l < 32; l++) {
                 Lane &ln = L[(size_t)w * 32 + l];
-                const uint32_t lt = (1u << l) - 1u;
-                const uint32_t s_in = cw.s ^ ((uint32_t)popc32(PB & lt) & 1u);
-                const uint32_t p_in = l ? ((NQ >> (l - 1)) & 1u) : cw.p;
-                ln.out = lane_structurals(ln.m, s_in, p_in);
-                err_unescaped |= ln.out.unescaped_err;
-                err_utf8 |= ln.u8err;
-                uint64_t st = ln.out.structural;
+                ln.rel = (uint32_t)popc32(PB & ((1u << l) - 1u)) & 1u;
+                const uint32_t p_in = l ? ((NQ >> (l - 1)) & 1u) : wst.p;
+                ln.d = lane_structurals_dual(ln.m, ln.q, ln.rel, p_in);
+                ln.c0 = (uint32_t)popc64(ln.d.m0);
+                ln.c1 = (uint32_t)popc64(ln.d.m1);
+                wc0[w] += ln.c0;
+                wc1[w] += ln.c1;
+                fl |= (ln.d.u0 << 1) | (ln.d.u1 << 2) | (ln.u8err << 3);
+            }
+            wflags[w] = fl | ((uint32_t)popc32(PB) & 1u);
+            if (w == warps - 1) tail = warp_lane_e_in(A, O, 32, wst.e) | ((NQ >> 31) << 1);
+        }
+        // ---- "warp 0": tile aggregate, look-back, prefix ----
+        TileAgg agg;
+        memset(&agg, 0, sizeof agg);
+        std::vector<uint32_t> R(warps), off0(warps), off1(warps);
+        uint32_t par = 0, run0 = 0, run1 = 0;
+        for (int w = 0; w < warps; w++) {
+            R[w] = par;
+            const uint32_t t0 = R[w] ? wc1[w] : wc0[w], t1 = R[w] ? wc0[w] : wc1[w];
+            off0[w] = run0;
+            off1[w] = run1;
+            run0 += t0;
+            run1 += t1;
+            agg.un[0] |= (wflags[w] >> (R[w] ? 2 : 1)) & 1u;
+            agg.un[1] |= (wflags[w] >> (R[w] ? 1 : 2)) & 1u;
+            agg.u8 |= (wflags[w] >> 3) & 1u;
+            par ^= wflags[w] & 1u;
+        }
+        agg.par = par;
+        agg.c[0] = run0;
+        agg.c[1] = run1;
+        agg.e_out = tail & 1u;
+        agg.p_out = (tail >> 1) & 1u;
+        d_agg[(size_t)tile] = desc_pack_agg(gen, agg);
+        if (desc_gen(d_agg[(size_t)tile]) != gen || desc_status(d_agg[(size_t)tile]) != DESC_AGG) return -100;
+        LookbackResult lb = {0, 0, 0};
+        if (tile > 0) lb = lookback(d_agg, d_prefix, shows_prefix, tile, 4);
+        const uint32_t s_in = lb.s_in & 1u;
+        const uint32_t total = agg.c[s_in];
+        TilePrefix pre;
+        pre.s_out = s_in ^ agg.par;
+        pre.e_out = agg.e_out;
+        pre.p_out = agg.p_out;
+        pre.err = lb.err | (agg.un[s_in] ? EF_UNESCAPED : 0u) | (agg.u8 ? EF_UTF8 : 0u);
+        pre.count = lb.base + total;
+        d_prefix[(size_t)tile] = desc_pack_prefix(gen, pre);
+        if (desc_gen(d_prefix[(size_t)tile]) != gen || desc_status(d_prefix[(size_t)tile]) != DESC_PREFIX) return -101;
+        // which kind later tiles will see for this tile: an irregular pattern, tile 0 always inclusive
+        shows_prefix[(size_t)tile] = (tile == 0) || ((tile * 7 + tile / 3) % 5 == 0);
+        d_either[(size_t)tile] = shows_prefix[(size_t)tile] ? d_prefix[(size_t)tile] : d_agg[(size_t)tile];
+        last = pre;
+        if (lb.base != total_written) return -102;  // the look-back must reproduce the running count
+        // ---- flatten ----
+        for (int w = 0; w < warps; w++) {
+            const uint32_t sw = s_in ^ R[w];
+            uint32_t rank = s_in ? off1[w] : off0[w];
+            for (int l = 0; l < 32; l++) {
+                Lane &ln = L[(size_t)w * 32 + l];
+                const uint32_t s_lane = sw & 1u;  // ln.rel is already folded into m0 / m1
+                uint64_t st = s_lane ? ln.d.m1 : ln.d.m0;
                 const int64_t g0 = tb + (int64_t)w * 2048 + (int64_t)l * 64;
                 while (st) {
                     int bit = __builtin_ctzll(st);
                     st &= st - 1;
-                    uint32_t v = (uint32_t)(g0 + bit - (int64_t)mis);
-                    if (total < cap) out[total] = v;
-                    total++;
+                    const uint64_t o = (uint64_t)lb.base + rank++;
+                    if (o < cap) out[o] = (uint32_t)(g0 + bit - (int64_t)mis);
                 }
             }
+            if (w == warps - 1 && rank != total) return -103;
         }
+        total_written += total;
     }
-    if (n_written_out) *n_written_out = total;
-    if (utf8_err_out) *utf8_err_out = (int32_t)err_utf8;
-    if (carry.s) return 15;
-    if (err_unescaped) return 14;
-    if (total + 3 > cap) return 1;
-    if (n_out) *n_out = (uint32_t)total;
-    out[total] = (uint32_t)len;
-    out[total + 1] = (uint32_t)len;
-    out[total + 2] = 0;
-    if (total == 0) return 13;
-    if ((flags & 1u) && err_utf8) return 11;
+    const uint64_t n = last.count;
+    if (n_written_out) *n_written_out = n;
+    if (utf8_err_out) *utf8_err_out = (last.err & EF_UTF8) ? 1 : 0;
+    if (last.s_out) return 15;
+    if (last.err & EF_UNESCAPED) return 14;
+    if (n + 3 > cap) return 1;
+    if (n_out) *n_out = (uint32_t)n;
+    out[n] = (uint32_t)len;
+    out[n + 1] = (uint32_t)len;
+    out[n + 2] = 0;
+    if (n == 0) return 13;
+    if ((flags & 1u) && (last.err & EF_UTF8)) return 11;
     return 0;
 }
 
-// direct checks of the transposition and classifier on arbitrary 32 bytes
+// direct checks of the transposition on arbitrary 32 bytes
 extern "C" void emu_bitplanes32(const uint8_t *bytes32, uint32_t *planes8) {
     uint32_t w[8];
     memcpy(w, bytes32, 32);
     bitplanes32(w, planes8);
 }
-
-extern "C" uint32_t emu_span_compose(uint32_t older, uint32_t newer) { return span_compose(older, newer); }

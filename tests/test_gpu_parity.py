@@ -145,7 +145,7 @@ def test_validate_utf8_flag_through_facade():
 # ------------------------------------------------------------------------------------------------
 # config 5: adversarial set, device-resident path, every tile shape, aligned and misaligned input
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("warps", [2, 4, 8])
+@pytest.mark.parametrize("warps", [2, 4, 8, 16, 32])
 def test_adversarial_corpus_device(dev, scratch, warps):
     tiles = tuple(sorted({warps * 2048, 4096}))
     corpus = cases.adversarial_cases(tile_bytes=tiles)
@@ -199,7 +199,7 @@ def test_capacity(dev, scratch):
 def test_dense_tile_takes_direct_path(dev, scratch):
     data = b"[" + b"1," * 100000 + b"1]"  # every byte structural: > 0.5 per byte, bypasses staging
     want = oracle.stage1(data, impl="fast")
-    for warps in (2, 8):
+    for warps in (2, 8, 16, 32):
         res, out = run_device(dev, scratch, data, warps=warps)
         assert_same(res, out, want)
 
@@ -243,7 +243,7 @@ def test_twitter_like_631k(dev):
     assert want.error == 0
     inp = torch.from_numpy(doc).cuda()
     out = torch.empty(doc.size + 3, dtype=torch.int32, device="cuda")
-    for warps in (0, 2, 4, 8):
+    for warps in (0, 2, 4, 8, 16, 32):
         dev.set_warps(warps)
         out.fill_(-1)
         res = dev.index(inp, out)
@@ -260,7 +260,7 @@ def test_document_64mib_full_compare(dev):
     assert want.error == 0
     inp = torch.from_numpy(doc).cuda()
     out = torch.empty(size // 3, dtype=torch.int32, device="cuda")
-    for warps in (2, 8):
+    for warps in (2, 8, 16, 32):
         dev.set_warps(warps)
         out.fill_(-1)
         res = dev.index(inp, out)
