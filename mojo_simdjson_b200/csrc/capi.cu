@@ -9,6 +9,7 @@
 
 #include "../../include/simdjson_b200.h"
 #include "stage1_kernel.cuh"
+#include "stage1_persistent.cuh"
 
 using namespace sjb200;
 
@@ -47,6 +48,9 @@ struct sjb200_ctx {
     uint32_t slot = 0;                  // slot used by the most recent launch
     uint32_t gen = 0;
     int forced_warps = 0;
+    int kernel_kind = 1;                // 0: one tile per CTA, 1: persistent warp-specialised
+    int sm_count = 0;
+    int persist_occ[3] = {0, 0, 0};     // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -71,6 +75,28 @@ cudaError_t prepare_cfg() {
         e = cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     cudaFuncSetAttribute(stage1_kernel<WARPS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
+template <int NW, bool UTF8>
+cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = PersistCfg<NW>;
+    const unsigned grid = p.ntiles < (unsigned)max_ctas ? p.ntiles : (unsigned)max_ctas;
+    stage1_persistent_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+template <int NW>
+cudaError_t prepare_persist(int *occ) {
+    using Cfg = PersistCfg<NW>;
+    cudaError_t e = cudaFuncSetAttribute(stage1_persistent_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stage1_persistent_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(stage1_persistent_kernel<NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_persistent_kernel<NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int a = 0, b = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_persistent_kernel<NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_persistent_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    *occ = a < b ? a : b;
+    if (*occ < 1) *occ = 1;
     return e;
 }
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 32; }
@@ -102,30 +128,49 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     p.out = d_idx;
     p.cap = cap;
     p.desc = c->desc;
-    p.ticket = c->ticket;
     p.result = c->d_results + slot;
     p.dev_status = d_status;
     c->gen = (c->gen + 1) & GEN_MASK;
-    if (c->gen == 0) {  // the 20-bit generation wrapped: clear the descriptors once (stream ordered), restart at 1
+    if (c->gen == 0) {  // the 20-bit generation wrapped: clear descriptors and tickets once (stream ordered), restart at 1
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
+        cudaMemsetAsync(c->ticket, 0, 256, c->stream);
         c->gen = 1;
     }
     p.gen = c->gen;
     p.flags = flags;
-    const int warps = pick_warps(c, p.alen);
+    int warps = pick_warps(c, p.alen);
+    static int env_kind = -1;
+    if (env_kind < 0) {
+        const char *e = getenv("SJB200_KERNEL");
+        env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : 1) : 2;
+    }
+    const int kind = env_kind == 2 ? c->kernel_kind : env_kind;
+    const bool persist = kind == 1 && warps <= 8;
     const uint64_t tile = (uint64_t)warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
     p.ntiles = (uint32_t)ntiles;
+    // ticket counters: [0],[1] alternate between successive persistent launches, [2] serves the one-tile-per-CTA kernel
+    p.ticket = persist ? c->ticket : c->ticket + 2;
     const bool utf8 = !(flags & SJB200_FLAG_NO_UTF8);
     cudaError_t e;
     if (c->timed) cudaEventRecord(c->ev0, c->stream);
-    switch (warps) {
-    case 32: e = utf8 ? launch_cfg<32, true>(p, c->stream) : launch_cfg<32, false>(p, c->stream); break;
-    case 16: e = utf8 ? launch_cfg<16, true>(p, c->stream) : launch_cfg<16, false>(p, c->stream); break;
-    case 8: e = utf8 ? launch_cfg<8, true>(p, c->stream) : launch_cfg<8, false>(p, c->stream); break;
-    case 4: e = utf8 ? launch_cfg<4, true>(p, c->stream) : launch_cfg<4, false>(p, c->stream); break;
-    default: e = utf8 ? launch_cfg<2, true>(p, c->stream) : launch_cfg<2, false>(p, c->stream); break;
+    if (persist) {
+        const int idx = warps == 8 ? 2 : (warps == 4 ? 1 : 0);
+        const int max_ctas = c->sm_count * c->persist_occ[idx];
+        switch (warps) {
+        case 8: e = utf8 ? launch_persist<8, true>(p, c->stream, max_ctas) : launch_persist<8, false>(p, c->stream, max_ctas); break;
+        case 4: e = utf8 ? launch_persist<4, true>(p, c->stream, max_ctas) : launch_persist<4, false>(p, c->stream, max_ctas); break;
+        default: e = utf8 ? launch_persist<2, true>(p, c->stream, max_ctas) : launch_persist<2, false>(p, c->stream, max_ctas); break;
+        }
+    } else {
+        switch (warps) {
+        case 32: e = utf8 ? launch_cfg<32, true>(p, c->stream) : launch_cfg<32, false>(p, c->stream); break;
+        case 16: e = utf8 ? launch_cfg<16, true>(p, c->stream) : launch_cfg<16, false>(p, c->stream); break;
+        case 8: e = utf8 ? launch_cfg<8, true>(p, c->stream) : launch_cfg<8, false>(p, c->stream); break;
+        case 4: e = utf8 ? launch_cfg<4, true>(p, c->stream) : launch_cfg<4, false>(p, c->stream); break;
+        default: e = utf8 ? launch_cfg<2, true>(p, c->stream) : launch_cfg<2, false>(p, c->stream); break;
+        }
     }
     if (c->timed) cudaEventRecord(c->ev1, c->stream);
     c->launches++;
@@ -212,6 +257,10 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_cfg<8>();
     if (e == cudaSuccess) e = prepare_cfg<16>();
     if (e == cudaSuccess) e = prepare_cfg<32>();
+    if (e == cudaSuccess) e = prepare_persist<2>(&c->persist_occ[0]);
+    if (e == cudaSuccess) e = prepare_persist<4>(&c->persist_occ[1]);
+    if (e == cudaSuccess) e = prepare_persist<8>(&c->persist_occ[2]);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         const int32_t code = cuda_err(e);

@@ -184,13 +184,20 @@ struct LookbackResult {
 };
 __device__ __forceinline__ LookbackResult lookback(const uint64_t *desc, uint32_t gen, int tile, int lane) {
     SpanAcc acc = span_empty();  // the already visited (newer) tiles as a function of the parity entering them
+    const uint32_t want = gen & GEN_MASK;
     int base = tile - 1;
+    uint64_t dnext = base - lane >= 0 ? ld_desc(desc + (base - lane)) : 0;
     while (true) {
         const int j = base - lane;
-        uint64_t d = 0;
+        uint64_t d = dnext;
+        // have the following window in flight before we start waiting on this one
+        dnext = j - 32 >= 0 ? ld_desc(desc + (j - 32)) : 0;
         uint32_t st = DESC_PREFIX;  // before the first tile: outside a string, nothing produced
         if (j >= 0) {
-            d = wait_desc(desc, j, gen);
+            while (desc_gen(d) != want) {
+                __nanosleep(20);
+                d = ld_desc(desc + j);
+            }
             st = desc_status(d);
         }
         const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == DESC_PREFIX);
@@ -225,6 +232,223 @@ __device__ __forceinline__ LookbackResult lookback(const uint64_t *desc, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
+// phase 1 of a warp: 2 KiB of shared-memory input -> per-lane dual structural masks + warp summary
+// ---------------------------------------------------------------------------------------------
+struct LaneInput {
+    uint32_t w[16];   // this lane's 64 bytes
+    uint32_t prev;    // the 4 bytes before them (UTF-8 look-behind)
+    PrevState wst;    // carries entering the warp
+    int64_t g0;       // aligned coordinate of the lane's first byte
+};
+struct LanePhase1 {
+    uint64_t m0, m1;  // structural bits if the warp starts outside / inside a string
+    uint32_t c0, c1;  // their popcounts
+    uint32_t v0;      // index value of bit 0
+    // warp-uniform
+    uint32_t wc0, wc1;
+    uint32_t wflags;  // bit0 quote parity, bit1/2 unescaped control (outside/inside), bit3 UTF-8 violation
+    uint32_t tail;    // bit0 e_out, bit1 p_out after the warp's last byte
+};
+
+// every shared-memory read of the input happens here (the persistent kernel frees the buffer right after)
+template <bool UTF8>
+__device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_tile, int warp, int lane, int tile, int64_t tb,
+                                          int tile_bytes, const Stage1Params &P) {
+    const int64_t alen = (int64_t)P.alen;
+    const int woff = warp * 2048;
+    const int off = woff + lane * 64;
+    in.g0 = tb + off;
+    const bool edge = (tile == 0) || (tb + tile_bytes > alen);
+    const uint4 *src = reinterpret_cast<const uint4 *>(smem_tile + off);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint4 v = src[q];
+        in.w[4 * q + 0] = v.x;
+        in.w[4 * q + 1] = v.y;
+        in.w[4 * q + 2] = v.z;
+        in.w[4 * q + 3] = v.w;
+    }
+    in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_tile + off - 4) : 0u;
+    if (edge) {  // only the first and last tile: bytes outside [mis, alen) read as 0x20 (reference tail padding)
+#pragma unroll
+        for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
+        if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
+    }
+    // carries entering the warp, from the bytes before it (warp 0: the halo / the previous tile)
+    in.wst = warp == 0 ? tile_prev_state(smem_tile, tile, lane, P.desc, P.gen)
+                       : warp_prev_state(smem_tile, woff, lane, tb, (int64_t)P.mis, alen, edge, tile, P.desc, P.gen);
+}
+
+template <bool UTF8>
+__device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P) {
+    const int64_t alen = (int64_t)P.alen;
+    LaneMasks m;
+    uint32_t u8err = 0;
+    {
+        uint32_t pl[8], ph[8];
+        bitplanes32(in.w, pl);
+        bitplanes32(in.w + 8, ph);
+        Classes32 cl, ch;
+        Utf8Pre32 ul, uh;
+        classify32<UTF8>(pl, cl, ul);
+        classify32<UTF8>(ph, ch, uh);
+        m.bs = join64(cl.bs, ch.bs);
+        m.rq = join64(cl.rq, ch.rq);
+        m.op = join64(cl.op, ch.op);
+        m.ws = join64(cl.ws, ch.ws);
+        m.ctl = join64(cl.ctl, ch.ctl);
+        if (UTF8) {
+            // whole-warp fast path: nothing >= 0x80 in these 2 KiB nor in the 4 bytes before each chunk
+            const bool any_hi = ((ul.hi | uh.hi) != 0) || ((in.prev & 0x80808080u) != 0);
+            if (__any_sync(0xFFFFFFFFu, any_hi)) {
+                const Utf8Carry uc = utf8_carry_from_prev_word(in.prev);
+                uint32_t tail_must;
+                const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
+                u8err = (ue != 0) || (in.g0 + 64 == alen && tail_must != 0);
+            }
+        }
+    }
+    // escapes and quotes, exact; structural bits for both in-string parities
+    const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
+    const uint32_t bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
+    const LaneQuotes q = lane_quotes(m, warp_lane_e_in(bA, bO, lane, in.wst.e));
+    const uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (q.ps >> 63) != 0);
+    const uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (q.nqs >> 63) != 0);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t rel = (uint32_t)__popc(bPB & lt) & 1u;
+    const uint32_t p_in = lane ? ((bNQ >> (lane - 1)) & 1u) : in.wst.p;
+    const LaneDual dual = lane_structurals_dual(m, q, rel, p_in);
+    r.m0 = dual.m0;
+    r.m1 = dual.m1;
+    r.c0 = (uint32_t)__popcll(dual.m0);
+    r.c1 = (uint32_t)__popcll(dual.m1);
+    r.v0 = (uint32_t)(in.g0 - (int64_t)P.mis);
+    r.wc0 = __reduce_add_sync(0xFFFFFFFFu, r.c0);
+    r.wc1 = __reduce_add_sync(0xFFFFFFFFu, r.c1);
+    r.wflags = __reduce_or_sync(0xFFFFFFFFu, (dual.u0 << 1) | (dual.u1 << 2) | (u8err << 3)) | ((uint32_t)__popc(bPB) & 1u);
+    r.tail = warp_lane_e_in(bA, bO, 32, in.wst.e) | ((bNQ >> 31) << 1);
+}
+
+// combine the warp summaries of a tile (called by one full warp): the tile aggregate, and for every warp (lane < nwarps)
+// the parity of the warps before it and its rank offsets for both tile parities
+__device__ __forceinline__ TileAgg tile_aggregate(uint32_t fl, uint32_t a0, uint32_t a1, uint32_t tail, int nwarps, int lane,
+                                                  uint32_t &R, uint32_t &off0, uint32_t &off1) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t parb = __ballot_sync(0xFFFFFFFFu, fl & 1u);
+    R = (uint32_t)__popc(parb & lt) & 1u;                  // parity of the warps before this one
+    const uint32_t t0 = R ? a1 : a0, t1 = R ? a0 : a1;     // this warp's count if the TILE starts outside / inside
+    uint32_t i0 = t0, i1 = t1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x0 = __shfl_up_sync(0xFFFFFFFFu, i0, d);
+        const uint32_t x1 = __shfl_up_sync(0xFFFFFFFFu, i1, d);
+        if (lane >= d) {
+            i0 += x0;
+            i1 += x1;
+        }
+    }
+    off0 = i0 - t0;
+    off1 = i1 - t1;
+    TileAgg agg;
+    agg.par = (uint32_t)__popc(parb) & 1u;
+    agg.c[0] = __shfl_sync(0xFFFFFFFFu, i0, nwarps - 1);
+    agg.c[1] = __shfl_sync(0xFFFFFFFFu, i1, nwarps - 1);
+    const uint32_t un0 = (fl >> (R ? 2 : 1)) & 1u, un1 = (fl >> (R ? 1 : 2)) & 1u;
+    const uint32_t eall = __reduce_or_sync(0xFFFFFFFFu, un0 | (un1 << 1) | (((fl >> 3) & 1u) << 2));
+    agg.un[0] = eall & 1u;
+    agg.un[1] = (eall >> 1) & 1u;
+    agg.u8 = (eall >> 2) & 1u;
+    agg.e_out = tail & 1u;
+    agg.p_out = (tail >> 1) & 1u;
+    return agg;
+}
+
+// finish(): reference json_structural_indexer.mojo:147-186, same priority order.  One thread of the last tile.
+__device__ __forceinline__ void write_verdict(const Stage1Params &P, const TilePrefix &pre) {
+    const uint64_t n = pre.count;
+    Stage1Result r;
+    r.n = (uint32_t)n;
+    r.n_written = (uint32_t)n;
+    r.n_valid = 0;
+    r.utf8_error = (pre.err & EF_UTF8) ? 1 : 0;
+    r.final_state = pre.s_out << 1;
+    r.reserved[0] = r.reserved[1] = 0;
+    if (pre.s_out) {
+        r.error = ERR_UNCLOSED_STRING;
+    } else if (pre.err & EF_UNESCAPED) {
+        r.error = ERR_UNESCAPED_CHARS;
+    } else if (n + 3 > P.cap) {
+        r.error = ERR_CAPACITY;
+    } else {
+        r.n_valid = 1;
+        P.out[n] = P.len;      // trailer: len, len, 0 (:167-173)
+        P.out[n + 1] = P.len;
+        P.out[n + 2] = 0;
+        if (n == 0) r.error = ERR_EMPTY;
+        else if ((P.flags & 1u) && (pre.err & EF_UTF8)) r.error = ERR_UTF8_ERROR;
+        else r.error = ERR_SUCCESS;
+    }
+    *P.result = r;
+    if (P.dev_status) {
+        P.dev_status[0] = r.error;
+        P.dev_status[1] = (int32_t)(r.n_valid ? r.n : 0u);
+    }
+}
+
+// flatten one lane's structural bits (BitIndexer.write, :46-58) into dst[0..]; bit-reversed so that one FLO finds the lowest
+__device__ __forceinline__ uint32_t *flatten_to(uint32_t *dst, uint64_t structural, uint32_t v0) {
+    uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
+    while (rlo) {
+        const int b = __clz((int)rlo);
+        *dst++ = v0 + (uint32_t)b;
+        rlo &= ~(0x80000000u >> b);
+    }
+    while (rhi) {
+        const int b = __clz((int)rhi);
+        *dst++ = v0 + 32u + (uint32_t)b;
+        rhi &= ~(0x80000000u >> b);
+    }
+    return dst;
+}
+__device__ __forceinline__ void flatten_direct(uint32_t *out, uint64_t cap, uint64_t o, uint64_t structural, uint32_t v0) {
+    uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
+    while (rlo) {
+        const int b = __clz((int)rlo);
+        if (o < cap) out[o] = v0 + (uint32_t)b;
+        o++;
+        rlo &= ~(0x80000000u >> b);
+    }
+    while (rhi) {
+        const int b = __clz((int)rhi);
+        if (o < cap) out[o] = v0 + 32u + (uint32_t)b;
+        o++;
+        rhi &= ~(0x80000000u >> b);
+    }
+}
+// copy staged indexes to global memory with 16-byte stores; stage[a .. a+total) holds out[first .. first+total),
+// a chosen so that stage and out share their 16-byte phase.  Executed by `nthreads` threads with ids tid.
+__device__ __forceinline__ void copy_out(const uint32_t *stage, uint32_t a, uint32_t total, uint32_t *out, uint64_t first,
+                                         uint64_t cap, uint32_t tid, uint32_t nthreads) {
+    const int64_t gbase = (int64_t)first - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
+    const uint32_t end = a + total;
+    const uint32_t nvec = (end + 3u) >> 2;
+    for (uint32_t v = tid; v < nvec; v += nthreads) {
+        const uint4 qv = reinterpret_cast<const uint4 *>(stage)[v];
+        const uint32_t j = 4u * v;
+        const int64_t g = gbase + (int64_t)j;
+        if (j >= a && j + 4u <= end && (uint64_t)(g + 4) <= cap) {
+            *reinterpret_cast<uint4 *>(out + g) = qv;
+        } else {
+            const uint32_t vals[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (j + i >= a && j + i < end && (uint64_t)(g + i) < cap) out[g + i] = vals[i];
+        }
+    }
+}
+__device__ __forceinline__ uint32_t out_phase(const uint32_t *out) { return (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u); }
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int WARPS>
@@ -237,7 +461,10 @@ struct TileCfg {
     static constexpr int SMEM_BYTES = (STAGE_CAP + 4) * 4;    // >= 16 + TILE
     static_assert(SMEM_BYTES >= 16 + TILE, "staging must cover the input tile");
     // resident CTAs per SM we ask the register allocator to allow (2048 threads / 64 K registers per SM)
-    static constexpr int MIN_CTAS = WARPS <= 4 ? 8 : (WARPS == 8 ? 4 : (WARPS == 16 ? 2 : 1));
+#ifndef SJ_MIN_CTAS_W8
+#define SJ_MIN_CTAS_W8 4
+#endif
+    static constexpr int MIN_CTAS = WARPS <= 4 ? 8 : (WARPS == 8 ? SJ_MIN_CTAS_W8 : (WARPS == 16 ? 2 : 1));
 };
 
 template <int WARPS, bool UTF8>
@@ -248,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wc0[WARPS], s_wc1[WARPS];   // warp counts if the warp starts outside / inside a string
-    __shared__ uint32_t s_wflags[WARPS];              // bit0 quote parity, bit1/2 unescaped-control (outside/inside), bit3 utf8
+    __shared__ uint32_t s_wflags[WARPS];
     __shared__ uint32_t s_woff[WARPS];                // rank of the warp's first index inside the tile (actual parity)
     __shared__ uint32_t s_ws[WARPS];                  // actual "starts inside a string" of each warp
     __shared__ uint32_t s_tail;                       // bit0 e_out, bit1 p_out of the tile
@@ -266,9 +493,8 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
     __syncthreads();
     const int tile = (int)s_tile;
     const int64_t tb = (int64_t)tile * TILE;               // aligned coordinate of the tile's first byte
-    const int64_t alen = (int64_t)P.alen;
     if (tid == 0) {
-        int64_t nbytes = alen - tb;
+        int64_t nbytes = (int64_t)P.alen - tb;
         nbytes = nbytes > TILE ? TILE : nbytes;
         nbytes = (nbytes + 15) & ~15ll;                     // stays inside the last 16-byte line of the data
         const uint32_t halo = tile > 0 ? 16u : 0u;          // 16 bytes of the previous tile (carry look-behind)
@@ -276,115 +502,28 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
         bulk_load(smem_u32(smem_raw) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar);
     }
     mbar_wait(bar, 0);
-    const uint8_t *smem_tile = smem_raw + 16;
 
-    // ---- this lane's 64 bytes -> masks ---------------------------------------------------------------
-    const int woff = warp * 2048;
-    const int off = woff + lane * 64;
-    const int64_t g0 = tb + off;
-    const bool edge = (tile == 0) || (tb + TILE > alen);
-    uint32_t w[16];
+    // ---- phase 1 ---------------------------------------------------------------------------------
+    LanePhase1 ph;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(smem_tile + off);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 v = src[q];
-            w[4 * q + 0] = v.x;
-            w[4 * q + 1] = v.y;
-            w[4 * q + 2] = v.z;
-            w[4 * q + 3] = v.w;
-        }
+        LaneInput in;
+        warp_load<UTF8>(in, smem_raw + 16, warp, lane, tile, tb, TILE, P);
+        warp_compute<UTF8>(ph, in, lane, P);
     }
-    uint32_t prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_tile + off - 4) : 0u;
-    if (edge) {  // only the first and last tile: bytes outside [mis, alen) read as 0x20 (reference tail padding)
-#pragma unroll
-        for (int k = 0; k < 16; k++) w[k] = mask_word(w[k], g0 + 4 * k, (int64_t)P.mis, alen);
-        if (UTF8) prev = (g0 == 0) ? 0x20202020u : mask_word(prev, g0 - 4, (int64_t)P.mis, alen);
-    }
-    // carries entering the warp, from the bytes before it (warp 0: the halo / the previous tile)
-    const PrevState wst = warp == 0 ? tile_prev_state(smem_tile, tile, lane, P.desc, P.gen)
-                                    : warp_prev_state(smem_tile, woff, lane, tb, (int64_t)P.mis, alen, edge, tile, P.desc, P.gen);
-
-    LaneMasks m;
-    uint32_t u8err = 0;
-    {
-        uint32_t pl[8], ph[8];
-        bitplanes32(w, pl);
-        bitplanes32(w + 8, ph);
-        Classes32 cl, ch;
-        Utf8Pre32 ul, uh;
-        classify32<UTF8>(pl, cl, ul);
-        classify32<UTF8>(ph, ch, uh);
-        m.bs = join64(cl.bs, ch.bs);
-        m.rq = join64(cl.rq, ch.rq);
-        m.op = join64(cl.op, ch.op);
-        m.ws = join64(cl.ws, ch.ws);
-        m.ctl = join64(cl.ctl, ch.ctl);
-        if (UTF8) {
-            // whole-warp fast path: nothing >= 0x80 in these 2 KiB nor in the 4 bytes before each chunk
-            const bool any_hi = ((ul.hi | uh.hi) != 0) || ((prev & 0x80808080u) != 0);
-            if (__any_sync(0xFFFFFFFFu, any_hi)) {
-                const Utf8Carry uc = utf8_carry_from_prev_word(prev);
-                uint32_t tail_must;
-                const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
-                u8err = (ue != 0) || (g0 + 64 == alen && tail_must != 0);
-            }
-        }
-    }
-    // escapes and quotes, exact; structural bits for both in-string parities
-    const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
-    const uint32_t bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
-    const LaneQuotes q = lane_quotes(m, warp_lane_e_in(bA, bO, lane, wst.e));
-    const uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (q.ps >> 63) != 0);
-    const uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (q.nqs >> 63) != 0);
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t rel = (uint32_t)__popc(bPB & lt) & 1u;
-    const uint32_t p_in = lane ? ((bNQ >> (lane - 1)) & 1u) : wst.p;
-    const LaneDual dual = lane_structurals_dual(m, q, rel, p_in);
-    const uint32_t c0 = (uint32_t)__popcll(dual.m0), c1 = (uint32_t)__popcll(dual.m1);
-    {
-        const uint32_t wc0 = __reduce_add_sync(0xFFFFFFFFu, c0);
-        const uint32_t wc1 = __reduce_add_sync(0xFFFFFFFFu, c1);
-        const uint32_t fl = __reduce_or_sync(0xFFFFFFFFu, (dual.u0 << 1) | (dual.u1 << 2) | (u8err << 3));
-        if (lane == 0) {
-            s_wc0[warp] = wc0;
-            s_wc1[warp] = wc1;
-            s_wflags[warp] = fl | ((uint32_t)__popc(bPB) & 1u);
-            if (warp == WARPS - 1) s_tail = warp_lane_e_in(bA, bO, 32, wst.e) | ((bNQ >> 31) << 1);
-        }
+    if (lane == 0) {
+        s_wc0[warp] = ph.wc0;
+        s_wc1[warp] = ph.wc1;
+        s_wflags[warp] = ph.wflags;
+        if (warp == WARPS - 1) s_tail = ph.tail;
     }
     __syncthreads();  // A: warp summaries visible; every lane has its bytes in registers (shared input is dead)
 
     // ---- warp 0: tile aggregate, look-back, inclusive prefix, verdict --------------------------------
     if (warp == 0) {
         const bool have = lane < WARPS;
-        const uint32_t fl = have ? s_wflags[lane] : 0u;
-        const uint32_t parb = __ballot_sync(0xFFFFFFFFu, fl & 1u);
-        const uint32_t R = (uint32_t)__popc(parb & lt) & 1u;  // parity of the warps before this one
-        const uint32_t a0 = have ? s_wc0[lane] : 0u, a1 = have ? s_wc1[lane] : 0u;
-        const uint32_t t0 = R ? a1 : a0, t1 = R ? a0 : a1;    // this warp's count if the TILE starts outside / inside
-        uint32_t i0 = t0, i1 = t1;
-#pragma unroll
-        for (int d = 1; d < WARPS; d <<= 1) {
-            const uint32_t x0 = __shfl_up_sync(0xFFFFFFFFu, i0, d);
-            const uint32_t x1 = __shfl_up_sync(0xFFFFFFFFu, i1, d);
-            if (lane >= d) {
-                i0 += x0;
-                i1 += x1;
-            }
-        }
-        TileAgg agg;
-        agg.par = (uint32_t)__popc(parb) & 1u;
-        agg.c[0] = __shfl_sync(0xFFFFFFFFu, i0, WARPS - 1);
-        agg.c[1] = __shfl_sync(0xFFFFFFFFu, i1, WARPS - 1);
-        const uint32_t un0 = (fl >> (R ? 2 : 1)) & 1u, un1 = (fl >> (R ? 1 : 2)) & 1u;
-        const uint32_t eall = __reduce_or_sync(0xFFFFFFFFu, un0 | (un1 << 1) | (((fl >> 3) & 1u) << 2));
-        agg.un[0] = eall & 1u;
-        agg.un[1] = (eall >> 1) & 1u;
-        agg.u8 = (eall >> 2) & 1u;
-        const uint32_t tail = s_tail;
-        agg.e_out = tail & 1u;
-        agg.p_out = (tail >> 1) & 1u;
+        uint32_t R, off0, off1;
+        const TileAgg agg = tile_aggregate(have ? s_wflags[lane] : 0u, have ? s_wc0[lane] : 0u, have ? s_wc1[lane] : 0u,
+                                           s_tail, WARPS, lane, R, off0, off1);
         LookbackResult lb = {0, 0, 0};
         if (tile > 0) {
             if (lane == 0) st_desc(P.desc + tile, desc_pack_agg(P.gen, agg));
@@ -400,52 +539,24 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
         pre.count = lb.base + total;
         if (lane == 0) st_desc(P.desc + tile, desc_pack_prefix(P.gen, pre));
         if (have) {
-            s_woff[lane] = s_in ? i1 - t1 : i0 - t0;
+            s_woff[lane] = s_in ? off1 : off0;
             s_ws[lane] = s_in ^ R;
         }
         if (lane == 0) {
             s_total = total;
             s_base = lb.base;
             if (tile == (int)P.ntiles - 1) {
-                // finish(): reference json_structural_indexer.mojo:147-186, same priority order
-                const uint64_t n = (uint64_t)lb.base + total;
-                Stage1Result r;
-                r.n = (uint32_t)n;
-                r.n_written = (uint32_t)n;
-                r.n_valid = 0;
-                r.utf8_error = (pre.err & EF_UTF8) ? 1 : 0;
-                r.final_state = pre.s_out << 1;
-                r.reserved[0] = r.reserved[1] = 0;
-                if (pre.s_out) {
-                    r.error = ERR_UNCLOSED_STRING;
-                } else if (pre.err & EF_UNESCAPED) {
-                    r.error = ERR_UNESCAPED_CHARS;
-                } else if (n + 3 > P.cap) {
-                    r.error = ERR_CAPACITY;
-                } else {
-                    r.n_valid = 1;
-                    P.out[n] = P.len;      // trailer: len, len, 0 (:167-173)
-                    P.out[n + 1] = P.len;
-                    P.out[n + 2] = 0;
-                    if (n == 0) r.error = ERR_EMPTY;
-                    else if ((P.flags & 1u) && (pre.err & EF_UTF8)) r.error = ERR_UTF8_ERROR;
-                    else r.error = ERR_SUCCESS;
-                }
-                *P.result = r;
-                if (P.dev_status) {
-                    P.dev_status[0] = r.error;
-                    P.dev_status[1] = (int32_t)(r.n_valid ? r.n : 0u);
-                }
+                write_verdict(P, pre);
                 *P.ticket = 0;  // every tile has drawn its ticket by now
             }
         }
     }
     __syncthreads();  // B: parity entering every warp and the output cursor are known
 
-    // ---- flatten: bitmask -> ascending uint32 indexes (BitIndexer.write, :46-58) -----------------------
-    const uint32_t s_lane = s_ws[warp] & 1u;   // the WARP starts inside a string? (the lane's own offset is already in m0/m1)
-    const uint64_t structural = s_lane ? dual.m1 : dual.m0;
-    const uint32_t cnt = s_lane ? c1 : c0;
+    // ---- flatten: bitmask -> ascending uint32 indexes ---------------------------------------------------
+    const uint32_t s_w = s_ws[warp] & 1u;   // the WARP starts inside a string? (the lane's own offset is already in m0/m1)
+    const uint64_t structural = s_w ? ph.m1 : ph.m0;
+    const uint32_t cnt = s_w ? ph.c1 : ph.c0;
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -454,57 +565,16 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
     }
     const uint32_t total = s_total, base = s_base;
     const uint32_t my = s_woff[warp] + incl - cnt;           // rank of this lane's first index inside the tile
-    const uint32_t v0 = (uint32_t)(g0 - (int64_t)P.mis);     // index value of bit 0 of the chunk
-    // bit-reversed words: clz finds the lowest structural, one FLO per index
-    uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
     if (total <= (uint32_t)Cfg::STAGE_CAP) {
         uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
         // keep shared and global 16-byte phases equal (the output pointer itself may be only 4-byte aligned)
-        const uint32_t a = (base + (uint32_t)((reinterpret_cast<uintptr_t>(P.out) >> 2) & 3u)) & 3u;
-        uint32_t *dst = stage + a + my;
-        while (rlo) {
-            const int b = __clz((int)rlo);
-            *dst++ = v0 + (uint32_t)b;
-            rlo &= ~(0x80000000u >> b);
-        }
-        while (rhi) {
-            const int b = __clz((int)rhi);
-            *dst++ = v0 + 32u + (uint32_t)b;
-            rhi &= ~(0x80000000u >> b);
-        }
+        const uint32_t a = (base + out_phase(P.out)) & 3u;
+        flatten_to(stage + a + my, structural, ph.v0);
         __syncthreads();  // C
-        // coalesced copy-out: vector v holds staged entries [4v, 4v+4) = global entries gbase + 4v ..
-        const int64_t gbase = (int64_t)base - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
-        const uint32_t end = a + total;
-        const uint32_t nvec = (end + 3u) >> 2;
-        for (uint32_t v = tid; v < nvec; v += Cfg::THREADS) {
-            const uint4 qv = reinterpret_cast<const uint4 *>(stage)[v];
-            const uint32_t j = 4u * v;
-            const int64_t g = gbase + (int64_t)j;
-            if (j >= a && j + 4u <= end && (uint64_t)(g + 4) <= P.cap) {
-                *reinterpret_cast<uint4 *>(P.out + g) = qv;
-            } else {
-                const uint32_t vals[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (j + i >= a && j + i < end && (uint64_t)(g + i) < P.cap) P.out[g + i] = vals[i];
-            }
-        }
+        copy_out(stage, a, total, P.out, base, P.cap, (uint32_t)tid, (uint32_t)Cfg::THREADS);
     } else {
-        // very dense tile (> 0.5 structurals per byte): write straight to global memory
-        uint64_t o = (uint64_t)base + my;
-        while (rlo) {
-            const int b = __clz((int)rlo);
-            if (o < P.cap) P.out[o] = v0 + (uint32_t)b;
-            o++;
-            rlo &= ~(0x80000000u >> b);
-        }
-        while (rhi) {
-            const int b = __clz((int)rhi);
-            if (o < P.cap) P.out[o] = v0 + 32u + (uint32_t)b;
-            o++;
-            rhi &= ~(0x80000000u >> b);
-        }
+        // very dense tile: write straight to global memory
+        flatten_direct(P.out, P.cap, (uint64_t)base + my, structural, ph.v0);
     }
 }
 

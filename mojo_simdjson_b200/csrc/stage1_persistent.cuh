@@ -1,0 +1,227 @@
+// stage1_persistent.cuh -- persistent, warp-specialised form of the stage-1 kernel.
+//
+// Same arithmetic and the same look-back descriptors as stage1_kernel.cuh; what changes is who waits for whom.
+// In the one-tile-per-CTA kernel every warp of a tile sits at a barrier while warp 0 walks the look-back chain
+// (measured: 43 % of all warp time).  Here a CTA is NW compute warps + 1 scan warp and loops over tiles drawn
+// from the ticket counter:
+//   scan warp    : draws the next ticket and issues its bulk copy (cp.async.bulk) as soon as the compute warps
+//                  have pulled the current tile into registers; then, for the current tile, runs the look-back,
+//                  publishes the inclusive prefix and hands (parity, output cursor) to the compute warps.
+//   compute warp : phase 1 of tile i (bytes -> dual structural masks), then flattens tile i-1, whose look-back
+//                  ran concurrently with phase 1 of tile i.  Indexes are staged per warp, so compute warps never
+//                  barrier with each other; the last warp to finish phase 1 publishes the tile aggregate itself, so
+//                  aggregates never queue behind a look-back.
+// All hand-offs are mbarriers in shared memory (SYNCS in SASS); there is no __syncthreads in the loop.
+#pragma once
+#include "stage1_kernel.cuh"
+
+namespace sjb200 {
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int NW>
+struct PersistCfg {
+    static constexpr int THREADS = (NW + 1) * 32;
+    static constexpr int TILE = NW * 2048;
+    static constexpr int WCAP = 512;                           // staged indexes per warp (density <= 0.25 per 2 KiB)
+    static constexpr int IN_BYTES = 16 + TILE;                 // halo + tile, single buffer
+    static constexpr int STAGE_BYTES = NW * (WCAP + 4) * 4;
+    static constexpr int SMEM_BYTES = ((IN_BYTES + 127) & ~127) + STAGE_BYTES;
+    static constexpr int MIN_CTAS = NW == 8 ? 4 : (NW == 4 ? 6 : 8);
+};
+
+struct TileSlot {                 // double-buffered hand-off between compute warps and the scan warp
+    uint32_t wc0[8], wc1[8], wflags[8];
+    uint32_t R[8], off0[8], off1[8];
+    uint64_t agg;                 // packed aggregate of the tile (what was published)
+    uint32_t tail;
+    uint32_t arrived;             // compute warps done with phase 1 of this tile
+    uint32_t s_in, base;          // from the look-back
+    int32_t tile;
+};
+
+template <int NW, bool UTF8>
+__global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage1_persistent_kernel(const Stage1Params P) {
+    using Cfg = PersistCfg<NW>;
+    constexpr int TILE = Cfg::TILE;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *smem_in = smem_raw;                                           // [0,16) halo, [16, 16+TILE) tile
+    uint32_t *smem_stage = reinterpret_cast<uint32_t *>(smem_raw + ((Cfg::IN_BYTES + 127) & ~127));
+    __shared__ __align__(8) uint64_t s_bar[6];  // 0 in_full, 1 in_empty, 2-3 sum_full[2], 4-5 carry_full[2]
+    __shared__ TileSlot s_slot[2];
+    __shared__ int32_t s_tile_of;               // tile held by the input buffer, -1 = no more work
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_in_full = smem_u32(&s_bar[0]), bar_in_empty = smem_u32(&s_bar[1]);
+    const uint32_t bar_sum = smem_u32(&s_bar[2]), bar_carry = smem_u32(&s_bar[4]);  // + 8 * slot
+
+    if (tid == 0) {
+        mbar_init(bar_in_full, 1);
+        mbar_init(bar_in_empty, NW);
+        mbar_init(bar_sum, 1);
+        mbar_init(bar_sum + 8, 1);
+        mbar_init(bar_carry, 1);
+        mbar_init(bar_carry + 8, 1);
+        s_slot[0].arrived = 0;
+        s_slot[1].arrived = 0;
+        fence_mbar_init();
+        // two ticket counters used alternately by successive launches: clear the one the NEXT launch will use
+        if (blockIdx.x == 0) P.ticket[(P.gen + 1) & 1u] = 0;
+    }
+    __syncthreads();
+    uint32_t *ticket = P.ticket + (P.gen & 1u);
+
+    if (warp == NW) {
+        // =============================== scan warp ===============================
+        // produce(): draw a ticket, start its bulk copy; returns the tile or -1
+        auto produce = [&]() -> int {
+            int t = -1;
+            if (lane == 0) {
+                const uint32_t k = atomicAdd(ticket, 1u);
+                if (k < P.ntiles) {
+                    t = (int)k;
+                    s_tile_of = t;
+                    const int64_t tb = (int64_t)t * TILE;
+                    int64_t nbytes = (int64_t)P.alen - tb;
+                    nbytes = nbytes > TILE ? TILE : nbytes;
+                    nbytes = (nbytes + 15) & ~15ll;
+                    const uint32_t halo = t > 0 ? 16u : 0u;
+                    mbar_expect_tx(bar_in_full, (uint32_t)nbytes + halo);
+                    bulk_load(smem_u32(smem_in) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar_in_full);
+                } else {
+                    s_tile_of = -1;
+                    mbar_arrive(bar_in_full);
+                }
+            }
+            return __shfl_sync(0xFFFFFFFFu, t, 0);
+        };
+        int cur = produce();
+        for (int i = 0; cur >= 0; i++) {
+            const int slot = i & 1;
+            const uint32_t par2 = (uint32_t)(i >> 1) & 1u;
+            // next tile: its bulk copy may start once every compute warp holds tile i in registers
+            mbar_wait(bar_in_empty, (uint32_t)i & 1u);
+            const int next = produce();
+            // tile i: aggregate was published by the last compute warp; run the look-back
+            mbar_wait(bar_sum + 8 * slot, par2);
+            TileSlot &S = s_slot[slot];
+            const TileAgg agg = desc_unpack_agg(S.agg);
+            LookbackResult lb = {0, 0, 0};
+            if (cur > 0) lb = lookback(P.desc, P.gen, cur, lane);
+            const uint32_t s_in = lb.s_in & 1u;
+            const uint32_t total = s_in ? agg.c[1] : agg.c[0];
+            TilePrefix pre;
+            pre.s_out = s_in ^ agg.par;
+            pre.e_out = agg.e_out;
+            pre.p_out = agg.p_out;
+            pre.err = lb.err | ((s_in ? agg.un[1] : agg.un[0]) ? EF_UNESCAPED : 0u) | (agg.u8 ? EF_UTF8 : 0u);
+            pre.count = lb.base + total;
+            if (lane == 0) {
+                st_desc(P.desc + cur, desc_pack_prefix(P.gen, pre));
+                S.s_in = s_in;
+                S.base = lb.base;
+                if (cur == (int)P.ntiles - 1) write_verdict(P, pre);
+                mbar_arrive(bar_carry + 8 * slot);  // release: S.s_in / S.base visible to the waiters
+            }
+            __syncwarp();
+            cur = next;
+        }
+    } else {
+        // =============================== compute warps ===============================
+        uint32_t *stage = smem_stage + warp * (Cfg::WCAP + 4);
+        LanePhase1 old;
+        old.m0 = old.m1 = 0;
+        old.c0 = old.c1 = old.v0 = 0;
+        bool have_old = false;
+        int i = 0;
+
+        // flatten tile i-1 (held in `old`) once its look-back has delivered parity and cursor
+        auto flush_old = [&](int it) {
+            const int slot = it & 1;
+            mbar_wait(bar_carry + 8 * slot, (uint32_t)(it >> 1) & 1u);
+            const TileSlot &S = s_slot[slot];
+            const uint32_t s_in = S.s_in & 1u;
+            const uint32_t s_w = (s_in ^ S.R[warp]) & 1u;
+            const uint64_t structural = s_w ? old.m1 : old.m0;
+            const uint32_t cnt = s_w ? old.c1 : old.c0;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint64_t first = (uint64_t)S.base + (s_in ? S.off1[warp] : S.off0[warp]);  // the warp's first index
+            if (wtotal <= (uint32_t)Cfg::WCAP) {
+                const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
+                flatten_to(stage + a + (incl - cnt), structural, old.v0);
+                __syncwarp();
+                copy_out(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane, 32u);
+                __syncwarp();  // the staging area is reused by the next tile
+            } else {
+                flatten_direct(P.out, P.cap, first + (incl - cnt), structural, old.v0);
+            }
+        };
+
+        while (true) {
+            mbar_wait(bar_in_full, (uint32_t)i & 1u);
+            const int tile = *reinterpret_cast<volatile int32_t *>(&s_tile_of);
+            if (tile < 0) break;
+            const int slot = i & 1;
+            const int64_t tb = (int64_t)tile * TILE;
+            LanePhase1 ph;
+            {
+                LaneInput in;
+                warp_load<UTF8>(in, smem_in + 16, warp, lane, tile, tb, TILE, P);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_in_empty);   // this warp no longer needs the input buffer
+                warp_compute<UTF8>(ph, in, lane, P);
+            }
+            TileSlot &S = s_slot[slot];
+            uint32_t order = 0;
+            if (lane == 0) {
+                S.wc0[warp] = ph.wc0;
+                S.wc1[warp] = ph.wc1;
+                S.wflags[warp] = ph.wflags;
+                if (warp == NW - 1) S.tail = ph.tail;
+                __threadfence_block();
+                order = atomicAdd(&S.arrived, 1u);
+            }
+            order = __shfl_sync(0xFFFFFFFFu, order, 0);
+            if (order == NW - 1) {
+                // last compute warp of the tile: build and publish the aggregate right away
+                __threadfence_block();
+                const bool have = lane < NW;
+                uint32_t R, off0, off1;
+                const TileAgg agg = tile_aggregate(have ? S.wflags[lane] : 0u, have ? S.wc0[lane] : 0u, have ? S.wc1[lane] : 0u,
+                                                   S.tail, NW, lane, R, off0, off1);
+                if (have) {
+                    S.R[lane] = R;
+                    S.off0[lane] = off0;
+                    S.off1[lane] = off1;
+                }
+                const uint64_t packed = desc_pack_agg(P.gen, agg);
+                if (lane == 0) {
+                    if (tile > 0) st_desc(P.desc + tile, packed);  // tile 0 goes straight to its prefix
+                    S.agg = packed;
+                    S.arrived = 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sum + 8 * slot);     // release: slot contents visible to the scan warp
+            }
+            if (have_old) flush_old(i - 1);
+            old = ph;
+            have_old = true;
+            i++;
+        }
+        if (have_old) flush_old(i - 1);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sjb200
