@@ -22,6 +22,9 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef SJ_SHR_FMA
+#define SJ_SHR_FMA 1
+#endif
 #if defined(__CUDACC__)
 #define SJ_HD __host__ __device__ __forceinline__
 #else
@@ -98,10 +101,29 @@ SJ_HD void byte_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint3
     o3 = prmt(t1, t3, 0x7632);
 }
 
+// (a & m) | (b & ~m) in ONE LOP3 (nvcc splits it in two when m is an immediate)
+SJ_HD uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+#else
+    return (a & m) | (b & ~m);
+#endif
+}
+// x >> s on the FMA pipe (IMAD.HI): the ALU pipe is the one this kernel saturates (profiles/b200_pipe_throughput_ubench.txt)
+SJ_HD uint32_t shr_fma(uint32_t x, int s) {
+#if defined(__CUDA_ARCH__) && SJ_SHR_FMA
+    return __umulhi(x, 1u << (32 - s));
+#else
+    return x >> s;
+#endif
+}
+
 // exchange the bit-field selected by ~m in a with the field selected by m in b (delta swap across regs)
 SJ_HD void field_swap(uint32_t &a, uint32_t &b, uint32_t m, int s) {
-    uint32_t na = (a & m) | ((b << s) & ~m);
-    uint32_t nb = ((a >> s) & m) | (b & ~m);
+    const uint32_t na = bitselect(a, b << s, m);
+    const uint32_t nb = bitselect(shr_fma(a, s), b, m);
     a = na;
     b = nb;
 }
@@ -267,9 +289,14 @@ SJ_HD uint64_t prefix_xor64(uint64_t x) {
 // that needs a global scan is s, the parity of all unescaped quotes before the position.
 // ------------------------------------------------------------------------------------------------
 SJ_HD uint32_t byte_is_scalar(uint32_t c) {  // !(op | whitespace), reference json_character_block.mojo:22-23
-    const bool ws = c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0D;
-    const bool op = c == 0x2C || c == 0x3A || c == 0x5B || c == 0x5D || c == 0x7B || c == 0x7D || c == 0x0C || c == 0x1A;
-    return !(ws || op);
+    // 128-bit membership table of the whitespace and op bytes (all < 0x80): 09 0A 0C 0D 1A | 20 2C 3A | 5B 5D | 7B 7D
+    const uint32_t t0 = (1u << 0x09) | (1u << 0x0A) | (1u << 0x0C) | (1u << 0x0D) | (1u << 0x1A);
+    const uint32_t t1 = (1u << 0x00) | (1u << 0x0C) | (1u << 0x1A);
+    uint32_t w = (1u << 0x1B) | (1u << 0x1D);  // 0x40..0x7F: 5B 5D and 7B 7D share one pattern
+    if (c < 0x40) w = t1;
+    if (c < 0x20) w = t0;
+    if (c >= 0x80) w = 0;
+    return ((w >> (c & 31u)) & 1u) ^ 1u;
 }
 
 struct PrevState {

@@ -22,6 +22,20 @@
 
 #include "stage1_core.cuh"
 
+// experiment knobs (defaults = the shipped configuration)
+#ifndef SJ_MBAR_HINT
+#define SJ_MBAR_HINT 0
+#endif
+#ifndef SJ_NSLEEP
+#define SJ_NSLEEP 20
+#endif
+#ifndef SJ_DEPTH
+#define SJ_DEPTH 1
+#endif
+#ifndef SJ_LEAN_FLATTEN
+#define SJ_LEAN_FLATTEN 0
+#endif
+
 namespace sjb200 {
 
 // simdjson error codes that stage 1 can produce (reference errors.mojo:2-34)
@@ -86,16 +100,21 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware until the phase completes or the time hint expires (no busy spin)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "SJ_WAIT:\n"
+#if SJ_MBAR_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra SJ_DONE;\n"
         "bra SJ_WAIT;\n"
         "SJ_DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"((uint32_t)SJ_MBAR_HINT)
         : "memory");
 }
 __device__ __forceinline__ uint64_t ld_desc(const uint64_t *p) {
@@ -110,7 +129,7 @@ __device__ __forceinline__ void st_desc(uint64_t *p, uint64_t v) {
 __device__ __forceinline__ uint64_t wait_desc(const uint64_t *desc, int j, uint32_t gen) {
     uint64_t d = ld_desc(desc + j);
     while (desc_gen(d) != (gen & GEN_MASK)) {
-        __nanosleep(20);
+        __nanosleep(SJ_NSLEEP);
         d = ld_desc(desc + j);
     }
     return d;
@@ -195,7 +214,7 @@ __device__ __forceinline__ LookbackResult lookback(const uint64_t *desc, uint32_
         uint32_t st = DESC_PREFIX;  // before the first tile: outside a string, nothing produced
         if (j >= 0) {
             while (desc_gen(d) != want) {
-                __nanosleep(20);
+                __nanosleep(SJ_NSLEEP);
                 d = ld_desc(desc + j);
             }
             st = desc_status(d);
@@ -395,20 +414,26 @@ __device__ __forceinline__ void write_verdict(const Stage1Params &P, const TileP
     }
 }
 
-// flatten one lane's structural bits (BitIndexer.write, :46-58) into dst[0..]; bit-reversed so that one FLO finds the lowest
-__device__ __forceinline__ uint32_t *flatten_to(uint32_t *dst, uint64_t structural, uint32_t v0) {
-    uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
-    while (rlo) {
-        const int b = __clz((int)rlo);
-        *dst++ = v0 + (uint32_t)b;
-        rlo &= ~(0x80000000u >> b);
+// flatten one lane's structural bits (BitIndexer.write, :46-58) into dst[0..].  The words are bit-reversed so that one
+// FLO finds the lowest structural; per index: FLO (XU) + subtract (value) + shift + and-with-predicate + store.
+__device__ __forceinline__ void flatten_word(uint32_t *&dst, uint32_t bits, uint32_t v31) {
+#if SJ_LEAN_FLATTEN
+    uint32_t r = __brev(bits);
+    while (r) {
+        const uint32_t h = 31u - (uint32_t)__clz((int)r);  // FLO: highest set bit of the reversed word
+        *dst++ = v31 - h;                                    // = v0 + (position of the lowest set bit)
+        r &= ~(1u << h);
     }
-    while (rhi) {
-        const int b = __clz((int)rhi);
-        *dst++ = v0 + 32u + (uint32_t)b;
-        rhi &= ~(0x80000000u >> b);
+#else
+    while (bits) {
+        *dst++ = v31 - 31u + (uint32_t)(__ffs((int)bits) - 1);
+        bits &= bits - 1;
     }
-    return dst;
+#endif
+}
+__device__ __forceinline__ void flatten_to(uint32_t *dst, uint64_t structural, uint32_t v0) {
+    flatten_word(dst, (uint32_t)structural, v0 + 31u);
+    flatten_word(dst, (uint32_t)(structural >> 32), v0 + 63u);
 }
 __device__ __forceinline__ void flatten_direct(uint32_t *out, uint64_t cap, uint64_t o, uint64_t structural, uint32_t v0) {
     uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
@@ -431,20 +456,41 @@ __device__ __forceinline__ void copy_out(const uint32_t *stage, uint32_t a, uint
                                          uint64_t cap, uint32_t tid, uint32_t nthreads) {
     const int64_t gbase = (int64_t)first - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
     const uint32_t end = a + total;
-    const uint32_t nvec = (end + 3u) >> 2;
-    for (uint32_t v = tid; v < nvec; v += nthreads) {
-        const uint4 qv = reinterpret_cast<const uint4 *>(stage)[v];
-        const uint32_t j = 4u * v;
-        const int64_t g = gbase + (int64_t)j;
-        if (j >= a && j + 4u <= end && (uint64_t)(g + 4) <= cap) {
-            *reinterpret_cast<uint4 *>(out + g) = qv;
-        } else {
-            const uint32_t vals[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (j + i >= a && j + i < end && (uint64_t)(g + i) < cap) out[g + i] = vals[i];
+    if (first + total <= cap) {                          // uniform: everything this call writes lies below the capacity
+        // whole 16-byte vectors
+        const uint32_t v_lo = (a + 3u) >> 2, v_hi = end >> 2;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
+        uint4 *gv = reinterpret_cast<uint4 *>(out + gbase);
+        for (uint32_t v = v_lo + tid; v < v_hi; v += nthreads) gv[v] = sv[v];
+        // ragged head (entries a .. 3) and tail (entries 4*v_hi .. end-1): at most 3 entries each, threads 0..3 / 4..7
+        if (tid < 8u) {
+            const uint32_t j = tid < 4u ? tid : 4u * v_hi + (tid - 4u);
+            const bool head = tid < 4u && j >= a && j < end && j < 4u * v_lo;
+            const bool tail = tid >= 4u && j < end && j >= a && v_hi >= v_lo;
+            if (head || tail) out[gbase + (int64_t)j] = stage[j];
+        }
+    } else {
+        for (uint32_t j = a + tid; j < end; j += nthreads) {
+            const int64_t g = gbase + (int64_t)j;
+            if ((uint64_t)g < cap) out[g] = stage[j];
         }
     }
+}
+// inclusive warp scan; the shuffle's in-range predicate guards the add (no compare / select per step)
+__device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t x) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        asm volatile(
+            "{\n"
+            ".reg .u32 t;\n"
+            ".reg .pred p;\n"
+            "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+            "@p add.u32 %0, %0, t;\n"
+            "}\n"
+            : "+r"(x)
+            : "r"(d));
+    }
+    return x;
 }
 __device__ __forceinline__ uint32_t out_phase(const uint32_t *out) { return (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u); }
 
@@ -557,12 +603,7 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
     const uint32_t s_w = s_ws[warp] & 1u;   // the WARP starts inside a string? (the lane's own offset is already in m0/m1)
     const uint64_t structural = s_w ? ph.m1 : ph.m0;
     const uint32_t cnt = s_w ? ph.c1 : ph.c0;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += t;
-    }
+    const uint32_t incl = warp_inclusive_sum(cnt);
     const uint32_t total = s_total, base = s_base;
     const uint32_t my = s_woff[warp] + incl - cnt;           // rank of this lane's first index inside the tile
     if (total <= (uint32_t)Cfg::STAGE_CAP) {

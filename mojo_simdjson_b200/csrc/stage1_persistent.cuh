@@ -51,23 +51,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *smem_in = smem_raw;                                           // [0,16) halo, [16, 16+TILE) tile
     uint32_t *smem_stage = reinterpret_cast<uint32_t *>(smem_raw + ((Cfg::IN_BYTES + 127) & ~127));
-    __shared__ __align__(8) uint64_t s_bar[6];  // 0 in_full, 1 in_empty, 2-3 sum_full[2], 4-5 carry_full[2]
-    __shared__ TileSlot s_slot[2];
+    constexpr int NS = 4;                        // hand-off slots (a tile is flushed two tiles after its phase 1)
+    __shared__ __align__(8) uint64_t s_bar[2 + 2 * NS];  // 0 in_full, 1 in_empty, 2.. sum_full[NS], 2+NS.. carry_full[NS]
+    __shared__ TileSlot s_slot[NS];
     __shared__ int32_t s_tile_of;               // tile held by the input buffer, -1 = no more work
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_in_full = smem_u32(&s_bar[0]), bar_in_empty = smem_u32(&s_bar[1]);
-    const uint32_t bar_sum = smem_u32(&s_bar[2]), bar_carry = smem_u32(&s_bar[4]);  // + 8 * slot
+    const uint32_t bar_sum = smem_u32(&s_bar[2]), bar_carry = smem_u32(&s_bar[2 + NS]);  // + 8 * slot
 
     if (tid == 0) {
         mbar_init(bar_in_full, 1);
         mbar_init(bar_in_empty, NW);
-        mbar_init(bar_sum, 1);
-        mbar_init(bar_sum + 8, 1);
-        mbar_init(bar_carry, 1);
-        mbar_init(bar_carry + 8, 1);
-        s_slot[0].arrived = 0;
-        s_slot[1].arrived = 0;
+        for (int k = 0; k < NS; k++) {
+            mbar_init(bar_sum + 8 * k, 1);
+            mbar_init(bar_carry + 8 * k, 1);
+            s_slot[k].arrived = 0;
+        }
         fence_mbar_init();
         // two ticket counters used alternately by successive launches: clear the one the NEXT launch will use
         if (blockIdx.x == 0) P.ticket[(P.gen + 1) & 1u] = 0;
@@ -101,8 +101,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
         };
         int cur = produce();
         for (int i = 0; cur >= 0; i++) {
-            const int slot = i & 1;
-            const uint32_t par2 = (uint32_t)(i >> 1) & 1u;
+            const int slot = i & (NS - 1);
+            const uint32_t par2 = (uint32_t)(i / NS) & 1u;
             // next tile: its bulk copy may start once every compute warp holds tile i in registers
             mbar_wait(bar_in_empty, (uint32_t)i & 1u);
             const int next = produce();
@@ -133,27 +133,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
     } else {
         // =============================== compute warps ===============================
         uint32_t *stage = smem_stage + warp * (Cfg::WCAP + 4);
-        LanePhase1 old;
-        old.m0 = old.m1 = 0;
-        old.c0 = old.c1 = old.v0 = 0;
-        bool have_old = false;
+        // the two previous tiles of this warp, waiting for their look-backs (registers)
+        struct Held {
+            uint64_t m0, m1;
+            uint32_t c0, c1, v0;
+        };
+        Held old1 = {0, 0, 0, 0, 0}, old2 = {0, 0, 0, 0, 0};  // tile i-1, tile i-2
+        int n_held = 0;
         int i = 0;
 
-        // flatten tile i-1 (held in `old`) once its look-back has delivered parity and cursor
-        auto flush_old = [&](int it) {
-            const int slot = it & 1;
-            mbar_wait(bar_carry + 8 * slot, (uint32_t)(it >> 1) & 1u);
+        // flatten a held tile (iteration `it`) once its look-back has delivered parity and cursor
+        auto flush_old = [&](const Held &old, int it) {
+            const int slot = it & (NS - 1);
+            mbar_wait(bar_carry + 8 * slot, (uint32_t)(it / NS) & 1u);
             const TileSlot &S = s_slot[slot];
             const uint32_t s_in = S.s_in & 1u;
             const uint32_t s_w = (s_in ^ S.R[warp]) & 1u;
             const uint64_t structural = s_w ? old.m1 : old.m0;
             const uint32_t cnt = s_w ? old.c1 : old.c0;
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += t;
-            }
+            const uint32_t incl = warp_inclusive_sum(cnt);
             const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const uint64_t first = (uint64_t)S.base + (s_in ? S.off1[warp] : S.off0[warp]);  // the warp's first index
             if (wtotal <= (uint32_t)Cfg::WCAP) {
@@ -171,7 +169,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
             mbar_wait(bar_in_full, (uint32_t)i & 1u);
             const int tile = *reinterpret_cast<volatile int32_t *>(&s_tile_of);
             if (tile < 0) break;
-            const int slot = i & 1;
+            const int slot = i & (NS - 1);
             const int64_t tb = (int64_t)tile * TILE;
             LanePhase1 ph;
             {
@@ -213,12 +211,26 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sum + 8 * slot);     // release: slot contents visible to the scan warp
             }
-            if (have_old) flush_old(i - 1);
-            old = ph;
-            have_old = true;
+            // flatten tile i-2: its look-back has had two phase-1 times to complete
+#if SJ_DEPTH == 1
+            if (n_held >= 1) {
+                flush_old(old1, i - 1);
+                n_held = 0;
+            }
+#else
+            if (n_held == 2) flush_old(old2, i - 2);
+#endif
+            old2 = old1;
+            old1.m0 = ph.m0;
+            old1.m1 = ph.m1;
+            old1.c0 = ph.c0;
+            old1.c1 = ph.c1;
+            old1.v0 = ph.v0;
+            if (n_held < 2) n_held++;
             i++;
         }
-        if (have_old) flush_old(i - 1);
+        if (n_held == 2) flush_old(old2, i - 2);
+        if (n_held >= 1) flush_old(old1, i - 1);
     }
 }
 
