@@ -50,13 +50,14 @@ struct sjb200_ctx {
     int forced_warps = 0;
     int kernel_kind = 1;                // 0: one tile per CTA, 1: persistent warp-specialised
     int sm_count = 0;
-    int persist_occ[3] = {0, 0, 0};     // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8
+    int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
     uint32_t last_flags = 0;
     bool pending = false;
     uint64_t *d_split = nullptr;        // scratch for batch_split_device
+    uint64_t *d_trace = nullptr;        // debug builds only
 };
 
 namespace {
@@ -99,7 +100,7 @@ cudaError_t prepare_persist(int *occ) {
     if (*occ < 1) *occ = 1;
     return e;
 }
-bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 32; }
+bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24 || w == 32; }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (c->forced_warps) return c->forced_warps;
@@ -111,6 +112,7 @@ int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     }
     if (env) return env;
     // small documents: smaller tiles so that the work spreads over all 148 SMs
+    if (alen >= (uint64_t)64 << 20) return 16;
     if (alen >= (uint64_t)148 * 4 * 16384) return 8;
     if (alen >= (uint64_t)148 * 4 * 8192) return 4;
     return 2;
@@ -130,6 +132,7 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     p.desc = c->desc;
     p.result = c->d_results + slot;
     p.dev_status = d_status;
+    p.trace = c->d_trace;
     c->gen = (c->gen + 1) & GEN_MASK;
     if (c->gen == 0) {  // the 20-bit generation wrapped: clear descriptors and tickets once (stream ordered), restart at 1
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
@@ -145,7 +148,7 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
         env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : 1) : 2;
     }
     const int kind = env_kind == 2 ? c->kernel_kind : env_kind;
-    const bool persist = kind == 1 && warps <= 8;
+    const bool persist = kind == 1 && warps <= 24;
     const uint64_t tile = (uint64_t)warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
@@ -156,9 +159,11 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     cudaError_t e;
     if (c->timed) cudaEventRecord(c->ev0, c->stream);
     if (persist) {
-        const int idx = warps == 8 ? 2 : (warps == 4 ? 1 : 0);
+        const int idx = warps == 24 ? 4 : (warps == 16 ? 3 : (warps == 8 ? 2 : (warps == 4 ? 1 : 0)));
         const int max_ctas = c->sm_count * c->persist_occ[idx];
         switch (warps) {
+        case 24: e = utf8 ? launch_persist<24, true>(p, c->stream, max_ctas) : launch_persist<24, false>(p, c->stream, max_ctas); break;
+        case 16: e = utf8 ? launch_persist<16, true>(p, c->stream, max_ctas) : launch_persist<16, false>(p, c->stream, max_ctas); break;
         case 8: e = utf8 ? launch_persist<8, true>(p, c->stream, max_ctas) : launch_persist<8, false>(p, c->stream, max_ctas); break;
         case 4: e = utf8 ? launch_persist<4, true>(p, c->stream, max_ctas) : launch_persist<4, false>(p, c->stream, max_ctas); break;
         default: e = utf8 ? launch_persist<2, true>(p, c->stream, max_ctas) : launch_persist<2, false>(p, c->stream, max_ctas); break;
@@ -250,6 +255,10 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
         c->d_out_cap = max_len_host + 3;
         if (e == cudaSuccess) e = cudaMalloc(&c->d_out, (size_t)(c->d_out_cap + 4) * 4);
     }
+#if SJ_TRACE
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_trace, (size_t)c->max_tiles * 16 * 8);
+    if (e == cudaSuccess) e = cudaMemset(c->d_trace, 0, (size_t)c->max_tiles * 16 * 8);
+#endif
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = prepare_cfg<2>();
@@ -260,6 +269,8 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_persist<2>(&c->persist_occ[0]);
     if (e == cudaSuccess) e = prepare_persist<4>(&c->persist_occ[1]);
     if (e == cudaSuccess) e = prepare_persist<8>(&c->persist_occ[2]);
+    if (e == cudaSuccess) e = prepare_persist<16>(&c->persist_occ[3]);
+    if (e == cudaSuccess) e = prepare_persist<24>(&c->persist_occ[4]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -281,6 +292,7 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     cudaFree(c->desc);
     cudaFree(c->ticket);
     cudaFree(c->d_split);
+    cudaFree(c->d_trace);
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -379,6 +391,14 @@ float sjb200_last_elapsed_ms(sjb200_ctx *c) {
 }
 
 uint64_t sjb200_launch_count(sjb200_ctx *c) { return c ? c->launches : 0; }
+
+// debug builds (-DSJ_TRACE=1) only: copies the per-tile timestamp trace (16 x u64 per tile) of the last launch
+int32_t sjb200_debug_trace(sjb200_ctx *c, uint64_t *host_out, uint64_t n_words) {
+    if (!c || !c->d_trace) return SJB200_UNINITIALIZED;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(host_out, c->d_trace, (size_t)n_words * 8, cudaMemcpyDeviceToHost));
+    return SJB200_SUCCESS;
+}
 
 int32_t sjb200_pinned_alloc(uint64_t bytes, void **p) {
     if (!p) return SJB200_UNINITIALIZED;

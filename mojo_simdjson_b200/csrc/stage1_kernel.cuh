@@ -32,6 +32,12 @@
 #ifndef SJ_DEPTH
 #define SJ_DEPTH 1
 #endif
+#ifndef SJ_PRODUCE_LATE
+#define SJ_PRODUCE_LATE 0
+#endif
+#ifndef SJ_TRACE
+#define SJ_TRACE 0
+#endif
 #ifndef SJ_LEAN_FLATTEN
 #define SJ_LEAN_FLATTEN 0
 #endif
@@ -75,6 +81,7 @@ struct Stage1Params {
     uint32_t gen;           // generation of this call (1 .. 2^20-1)
     uint32_t ntiles;
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
+    uint64_t *trace;        // debug builds (-DSJ_TRACE=1): 16 x u64 of timestamps per tile, else unused
 };
 
 #if defined(__CUDACC__)
@@ -82,6 +89,16 @@ struct Stage1Params {
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t gtime() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#if SJ_TRACE
+#define TRACE(P, tile, slot, val) do { if ((P).trace) (P).trace[(size_t)(tile) * 16 + (slot)] = (val); } while (0)
+#else
+#define TRACE(P, tile, slot, val) do { } while (0)
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

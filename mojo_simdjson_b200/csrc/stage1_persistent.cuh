@@ -4,13 +4,14 @@
 // In the one-tile-per-CTA kernel every warp of a tile sits at a barrier while warp 0 walks the look-back chain
 // (measured: 43 % of all warp time).  Here a CTA is NW compute warps + 1 scan warp and loops over tiles drawn
 // from the ticket counter:
-//   scan warp    : draws the next ticket and issues its bulk copy (cp.async.bulk) as soon as the compute warps
-//                  have pulled the current tile into registers; then, for the current tile, runs the look-back,
-//                  publishes the inclusive prefix and hands (parity, output cursor) to the compute warps.
+//   scan warp    : for every tile of the CTA, runs the look-back, publishes the inclusive prefix and hands
+//                  (parity, output cursor) to the compute warps.  It does nothing else, so a slow look-back never
+//                  delays a load or an aggregate.
 //   compute warp : phase 1 of tile i (bytes -> dual structural masks), then flattens tile i-1, whose look-back
 //                  ran concurrently with phase 1 of tile i.  Indexes are staged per warp, so compute warps never
-//                  barrier with each other; the last warp to finish phase 1 publishes the tile aggregate itself, so
-//                  aggregates never queue behind a look-back.
+//                  barrier with each other; the last warp to finish phase 1 publishes the tile aggregate itself, and
+//                  the last warp to pull a tile into registers draws the next ticket and starts its bulk copy
+//                  (cp.async.bulk), so the copy overlaps the whole of phase 1.
 // All hand-offs are mbarriers in shared memory (SYNCS in SASS); there is no __syncthreads in the loop.
 #pragma once
 #include "stage1_kernel.cuh"
@@ -31,12 +32,12 @@ struct PersistCfg {
     static constexpr int IN_BYTES = 16 + TILE;                 // halo + tile, single buffer
     static constexpr int STAGE_BYTES = NW * (WCAP + 4) * 4;
     static constexpr int SMEM_BYTES = ((IN_BYTES + 127) & ~127) + STAGE_BYTES;
-    static constexpr int MIN_CTAS = NW == 8 ? 4 : (NW == 4 ? 6 : 8);
+    static constexpr int MIN_CTAS = NW >= 24 ? 1 : (NW == 16 ? 2 : (NW == 8 ? 4 : (NW == 4 ? 6 : 8)));
 };
 
 struct TileSlot {                 // double-buffered hand-off between compute warps and the scan warp
-    uint32_t wc0[8], wc1[8], wflags[8];
-    uint32_t R[8], off0[8], off1[8];
+    uint32_t wc0[32], wc1[32], wflags[32];
+    uint32_t R[32], off0[32], off1[32];
     uint64_t agg;                 // packed aggregate of the tile (what was published)
     uint32_t tail;
     uint32_t arrived;             // compute warps done with phase 1 of this tile
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
     __shared__ __align__(8) uint64_t s_bar[2 + 2 * NS];  // 0 in_full, 1 in_empty, 2.. sum_full[NS], 2+NS.. carry_full[NS]
     __shared__ TileSlot s_slot[NS];
     __shared__ int32_t s_tile_of;               // tile held by the input buffer, -1 = no more work
+    __shared__ uint32_t s_loaded;               // compute warps that have pulled the current tile into registers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_in_full = smem_u32(&s_bar[0]), bar_in_empty = smem_u32(&s_bar[1]);
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
     if (tid == 0) {
         mbar_init(bar_in_full, 1);
         mbar_init(bar_in_empty, NW);
+        s_loaded = 0;
         for (int k = 0; k < NS; k++) {
             mbar_init(bar_sum + 8 * k, 1);
             mbar_init(bar_carry + 8 * k, 1);
@@ -75,40 +78,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
     __syncthreads();
     uint32_t *ticket = P.ticket + (P.gen & 1u);
 
+    // produce(it): one thread draws the ticket of iteration `it` and starts its bulk copy into the (free) input buffer;
+    // when the tickets are exhausted it wakes the compute warps and the scan warp with "no more work"
+    auto produce = [&](int it) {
+        const uint32_t k = atomicAdd(ticket, 1u);
+        if (k < P.ntiles) {
+            const int t = (int)k;
+            s_tile_of = t;
+            TRACE(P, t, 0, gtime());  // ticket drawn / copy issued
+            const int64_t tb = (int64_t)t * TILE;
+            int64_t nbytes = (int64_t)P.alen - tb;
+            nbytes = nbytes > TILE ? TILE : nbytes;
+            nbytes = (nbytes + 15) & ~15ll;
+            const uint32_t halo = t > 0 ? 16u : 0u;
+            mbar_expect_tx(bar_in_full, (uint32_t)nbytes + halo);
+            bulk_load(smem_u32(smem_in) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar_in_full);
+        } else {
+            s_tile_of = -1;
+            s_slot[it & (NS - 1)].tile = -1;
+            mbar_arrive(bar_in_full);
+            mbar_arrive(bar_sum + 8 * (it & (NS - 1)));
+        }
+    };
+    if (tid == 0) produce(0);
+
     if (warp == NW) {
         // =============================== scan warp ===============================
-        // produce(): draw a ticket, start its bulk copy; returns the tile or -1
-        auto produce = [&]() -> int {
-            int t = -1;
-            if (lane == 0) {
-                const uint32_t k = atomicAdd(ticket, 1u);
-                if (k < P.ntiles) {
-                    t = (int)k;
-                    s_tile_of = t;
-                    const int64_t tb = (int64_t)t * TILE;
-                    int64_t nbytes = (int64_t)P.alen - tb;
-                    nbytes = nbytes > TILE ? TILE : nbytes;
-                    nbytes = (nbytes + 15) & ~15ll;
-                    const uint32_t halo = t > 0 ? 16u : 0u;
-                    mbar_expect_tx(bar_in_full, (uint32_t)nbytes + halo);
-                    bulk_load(smem_u32(smem_in) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar_in_full);
-                } else {
-                    s_tile_of = -1;
-                    mbar_arrive(bar_in_full);
-                }
-            }
-            return __shfl_sync(0xFFFFFFFFu, t, 0);
-        };
-        int cur = produce();
-        for (int i = 0; cur >= 0; i++) {
+        for (int i = 0;; i++) {
             const int slot = i & (NS - 1);
-            const uint32_t par2 = (uint32_t)(i / NS) & 1u;
-            // next tile: its bulk copy may start once every compute warp holds tile i in registers
-            mbar_wait(bar_in_empty, (uint32_t)i & 1u);
-            const int next = produce();
-            // tile i: aggregate was published by the last compute warp; run the look-back
-            mbar_wait(bar_sum + 8 * slot, par2);
+            mbar_wait(bar_sum + 8 * slot, (uint32_t)(i / NS) & 1u);
             TileSlot &S = s_slot[slot];
+            const int cur = *reinterpret_cast<volatile int32_t *>(&S.tile);
+            if (cur < 0) break;
+            TRACE(P, cur, 3, gtime());  // look-back starts
             const TileAgg agg = desc_unpack_agg(S.agg);
             LookbackResult lb = {0, 0, 0};
             if (cur > 0) lb = lookback(P.desc, P.gen, cur, lane);
@@ -125,10 +127,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                 S.s_in = s_in;
                 S.base = lb.base;
                 if (cur == (int)P.ntiles - 1) write_verdict(P, pre);
+                TRACE(P, cur, 4, gtime());  // look-back done
                 mbar_arrive(bar_carry + 8 * slot);  // release: S.s_in / S.base visible to the waiters
             }
             __syncwarp();
-            cur = next;
         }
     } else {
         // =============================== compute warps ===============================
@@ -145,8 +147,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
         // flatten a held tile (iteration `it`) once its look-back has delivered parity and cursor
         auto flush_old = [&](const Held &old, int it) {
             const int slot = it & (NS - 1);
+#if SJ_TRACE
+            const uint64_t tc0 = gtime();
+#endif
             mbar_wait(bar_carry + 8 * slot, (uint32_t)(it / NS) & 1u);
             const TileSlot &S = s_slot[slot];
+#if SJ_TRACE
+            if (lane == 0 && (warp == 0 || warp == NW - 1)) { TRACE(P, S.tile, warp == 0 ? 8 : 9, gtime() - tc0); TRACE(P, S.tile, warp == 0 ? 10 : 11, gtime()); }  // carry wait, flush start
+#endif
             const uint32_t s_in = S.s_in & 1u;
             const uint32_t s_w = (s_in ^ S.R[warp]) & 1u;
             const uint64_t structural = s_w ? old.m1 : old.m0;
@@ -160,23 +168,41 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                 __syncwarp();
                 copy_out(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane, 32u);
                 __syncwarp();  // the staging area is reused by the next tile
+#if SJ_TRACE
+                if (lane == 0 && (warp == 0 || warp == NW - 1)) TRACE(P, S.tile, warp == 0 ? 12 : 13, gtime());  // flush done
+#endif
             } else {
                 flatten_direct(P.out, P.cap, first + (incl - cnt), structural, old.v0);
             }
         };
 
         while (true) {
+#if SJ_TRACE
+            const uint64_t tw0 = gtime();
+#endif
             mbar_wait(bar_in_full, (uint32_t)i & 1u);
             const int tile = *reinterpret_cast<volatile int32_t *>(&s_tile_of);
             if (tile < 0) break;
+#if SJ_TRACE
+            if (lane == 0 && (warp == 0 || warp == NW - 1)) { TRACE(P, tile, warp == 0 ? 5 : 6, gtime() - tw0); TRACE(P, tile, warp == 0 ? 1 : 7, gtime()); }  // input wait, phase-1 start
+#endif
             const int slot = i & (NS - 1);
             const int64_t tb = (int64_t)tile * TILE;
             LanePhase1 ph;
             {
                 LaneInput in;
                 warp_load<UTF8>(in, smem_in + 16, warp, lane, tile, tb, TILE, P);
+#if !SJ_PRODUCE_LATE
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_in_empty);   // this warp no longer needs the input buffer
+                if (lane == 0) {                            // this warp no longer needs the input buffer
+                    __threadfence_block();
+                    if (atomicAdd(&s_loaded, 1u) == NW - 1) {
+                        s_loaded = 0;                       // everyone has it in registers: refill the buffer now
+                        __threadfence_block();
+                        produce(i + 1);
+                    }
+                }
+#endif
                 warp_compute<UTF8>(ph, in, lane, P);
             }
             TileSlot &S = s_slot[slot];
@@ -205,8 +231,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                 const uint64_t packed = desc_pack_agg(P.gen, agg);
                 if (lane == 0) {
                     if (tile > 0) st_desc(P.desc + tile, packed);  // tile 0 goes straight to its prefix
+                    TRACE(P, tile, 2, gtime());  // aggregate published
                     S.agg = packed;
+                    S.tile = tile;
                     S.arrived = 0;
+#if SJ_PRODUCE_LATE
+                    produce(i + 1);  // ticket order == aggregate publication order: successors never wait long for us
+#endif
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sum + 8 * slot);     // release: slot contents visible to the scan warp
