@@ -58,6 +58,13 @@ struct sjb200_ctx {
     bool pending = false;
     uint64_t *d_split = nullptr;        // scratch for batch_split_device
     uint64_t *d_trace = nullptr;        // debug builds only
+    uint32_t launch_seq = 0;            // alternates the persistent kernel's ticket counters
+    // streaming host path: second stream for the device-to-host copies, one event + one mapped progress word per chunk
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_CHUNKS = 256;
+    cudaEvent_t chunk_ev[MAX_CHUNKS] = {};
+    uint32_t *h_progress = nullptr, *d_progress = nullptr;
+    uint64_t chunk_bytes = 32ull << 20;
 };
 
 namespace {
@@ -65,7 +72,7 @@ namespace {
 template <int WARPS, bool UTF8>
 cudaError_t launch_cfg(const Stage1Params &p, cudaStream_t s) {
     using Cfg = TileCfg<WARPS>;
-    stage1_kernel<WARPS, UTF8><<<p.ntiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    stage1_kernel<WARPS, UTF8><<<p.tile_end - p.tile_begin, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
 }
 template <int WARPS>
@@ -81,7 +88,8 @@ cudaError_t prepare_cfg() {
 template <int NW, bool UTF8>
 cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = PersistCfg<NW>;
-    const unsigned grid = p.ntiles < (unsigned)max_ctas ? p.ntiles : (unsigned)max_ctas;
+    const unsigned span = p.tile_end - p.tile_begin;
+    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
     stage1_persistent_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
 }
@@ -118,10 +126,18 @@ int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     return 2;
 }
 
-// enqueue one stage-1 kernel; the result lands in result slot `slot`
-int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap, uint32_t flags,
-                uint32_t slot, int32_t *d_status = nullptr) {
+// Describes one document: geometry, tile shape and generation.  A document is indexed by one launch (tile range =
+// everything) or, on the streaming host path, by several launches over consecutive tile ranges sharing the generation.
+struct DocPlan {
     Stage1Params p;
+    int warps;
+    bool persist;
+    bool utf8;
+};
+
+int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap,
+                      uint32_t flags, uint32_t slot, int32_t *d_status) {
+    Stage1Params &p = d.p;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
     p.mis = (uint32_t)(addr & 15u);
     p.abase = d_buf - p.mis;
@@ -133,6 +149,7 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     p.result = c->d_results + slot;
     p.dev_status = d_status;
     p.trace = c->d_trace;
+    p.progress = nullptr;
     c->gen = (c->gen + 1) & GEN_MASK;
     if (c->gen == 0) {  // the 20-bit generation wrapped: clear descriptors and tickets once (stream ordered), restart at 1
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
@@ -141,45 +158,69 @@ int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_i
     }
     p.gen = c->gen;
     p.flags = flags;
-    int warps = pick_warps(c, p.alen);
+    d.warps = pick_warps(c, p.alen);
     static int env_kind = -1;
     if (env_kind < 0) {
         const char *e = getenv("SJB200_KERNEL");
         env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : 1) : 2;
     }
     const int kind = env_kind == 2 ? c->kernel_kind : env_kind;
-    const bool persist = kind == 1 && warps <= 24;
-    const uint64_t tile = (uint64_t)warps * 2048;
+    d.persist = kind == 1 && d.warps <= 24;
+    const uint64_t tile = (uint64_t)d.warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
     p.ntiles = (uint32_t)ntiles;
+    p.tile_begin = 0;
+    p.tile_end = p.ntiles;
     // ticket counters: [0],[1] alternate between successive persistent launches, [2] serves the one-tile-per-CTA kernel
-    p.ticket = persist ? c->ticket : c->ticket + 2;
-    const bool utf8 = !(flags & SJB200_FLAG_NO_UTF8);
+    p.ticket = d.persist ? c->ticket : c->ticket + 2;
+    d.utf8 = !(flags & SJB200_FLAG_NO_UTF8);
+    return SJB200_SUCCESS;
+}
+
+// launch the tiles [tile_begin, tile_end) of a planned document on `stream`
+int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t tile_end, uint32_t *progress, cudaStream_t stream) {
+    Stage1Params p = d.p;
+    p.tile_begin = tile_begin;
+    p.tile_end = tile_end;
+    p.progress = progress;
+    p.ticket_sel = d.persist ? (c->launch_seq++ & 1u) : 0u;  // only persistent launches alternate the two counters
+    const int warps = d.warps;
+    const bool utf8 = d.utf8;
     cudaError_t e;
-    if (c->timed) cudaEventRecord(c->ev0, c->stream);
-    if (persist) {
+    if (d.persist) {
         const int idx = warps == 24 ? 4 : (warps == 16 ? 3 : (warps == 8 ? 2 : (warps == 4 ? 1 : 0)));
         const int max_ctas = c->sm_count * c->persist_occ[idx];
         switch (warps) {
-        case 24: e = utf8 ? launch_persist<24, true>(p, c->stream, max_ctas) : launch_persist<24, false>(p, c->stream, max_ctas); break;
-        case 16: e = utf8 ? launch_persist<16, true>(p, c->stream, max_ctas) : launch_persist<16, false>(p, c->stream, max_ctas); break;
-        case 8: e = utf8 ? launch_persist<8, true>(p, c->stream, max_ctas) : launch_persist<8, false>(p, c->stream, max_ctas); break;
-        case 4: e = utf8 ? launch_persist<4, true>(p, c->stream, max_ctas) : launch_persist<4, false>(p, c->stream, max_ctas); break;
-        default: e = utf8 ? launch_persist<2, true>(p, c->stream, max_ctas) : launch_persist<2, false>(p, c->stream, max_ctas); break;
+        case 24: e = utf8 ? launch_persist<24, true>(p, stream, max_ctas) : launch_persist<24, false>(p, stream, max_ctas); break;
+        case 16: e = utf8 ? launch_persist<16, true>(p, stream, max_ctas) : launch_persist<16, false>(p, stream, max_ctas); break;
+        case 8: e = utf8 ? launch_persist<8, true>(p, stream, max_ctas) : launch_persist<8, false>(p, stream, max_ctas); break;
+        case 4: e = utf8 ? launch_persist<4, true>(p, stream, max_ctas) : launch_persist<4, false>(p, stream, max_ctas); break;
+        default: e = utf8 ? launch_persist<2, true>(p, stream, max_ctas) : launch_persist<2, false>(p, stream, max_ctas); break;
         }
     } else {
         switch (warps) {
-        case 32: e = utf8 ? launch_cfg<32, true>(p, c->stream) : launch_cfg<32, false>(p, c->stream); break;
-        case 16: e = utf8 ? launch_cfg<16, true>(p, c->stream) : launch_cfg<16, false>(p, c->stream); break;
-        case 8: e = utf8 ? launch_cfg<8, true>(p, c->stream) : launch_cfg<8, false>(p, c->stream); break;
-        case 4: e = utf8 ? launch_cfg<4, true>(p, c->stream) : launch_cfg<4, false>(p, c->stream); break;
-        default: e = utf8 ? launch_cfg<2, true>(p, c->stream) : launch_cfg<2, false>(p, c->stream); break;
+        case 32: e = utf8 ? launch_cfg<32, true>(p, stream) : launch_cfg<32, false>(p, stream); break;
+        case 16: e = utf8 ? launch_cfg<16, true>(p, stream) : launch_cfg<16, false>(p, stream); break;
+        case 8: e = utf8 ? launch_cfg<8, true>(p, stream) : launch_cfg<8, false>(p, stream); break;
+        case 4: e = utf8 ? launch_cfg<4, true>(p, stream) : launch_cfg<4, false>(p, stream); break;
+        default: e = utf8 ? launch_cfg<2, true>(p, stream) : launch_cfg<2, false>(p, stream); break;
         }
     }
-    if (c->timed) cudaEventRecord(c->ev1, c->stream);
     c->launches++;
     return cuda_err(e);
+}
+
+// enqueue one stage-1 kernel over a whole document; the result lands in result slot `slot`
+int32_t enqueue(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap, uint32_t flags,
+                uint32_t slot, int32_t *d_status = nullptr) {
+    DocPlan d;
+    int32_t rc = plan_document(c, d, d_buf, len, d_idx, cap, flags, slot, d_status);
+    if (rc != SJB200_SUCCESS) return rc;
+    if (c->timed) cudaEventRecord(c->ev0, c->stream);
+    rc = launch_range(c, d, 0, d.p.ntiles, nullptr, c->stream);
+    if (c->timed) cudaEventRecord(c->ev1, c->stream);
+    return rc;
 }
 
 int32_t check_args(sjb200_ctx *c, uint64_t len, uint32_t flags) {
@@ -259,6 +300,14 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = cudaMalloc(&c->d_trace, (size_t)c->max_tiles * 16 * 8);
     if (e == cudaSuccess) e = cudaMemset(c->d_trace, 0, (size_t)c->max_tiles * 16 * 8);
 #endif
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < sjb200_ctx::MAX_CHUNKS && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_progress, 4 * sjb200_ctx::MAX_CHUNKS, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->d_progress, c->h_progress, 0);
+    if (e == cudaSuccess) {
+        const char *cb = getenv("SJB200_CHUNK_MIB");
+        if (cb && atoi(cb) > 0) c->chunk_bytes = (uint64_t)atoi(cb) << 20;
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = prepare_cfg<2>();
@@ -294,6 +343,10 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     cudaFree(c->d_split);
     cudaFree(c->d_trace);
     if (c->h_results) cudaFreeHost(c->h_results);
+    if (c->h_progress) cudaFreeHost(c->h_progress);
+    for (int k = 0; k < sjb200_ctx::MAX_CHUNKS; k++)
+        if (c->chunk_ev[k]) cudaEventDestroy(c->chunk_ev[k]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -357,20 +410,49 @@ int32_t sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, uint64_t len, uint32_t 
     if (rc != SJB200_SUCCESS) return rc;
     if (len > c->max_len_host || !c->d_in) return SJB200_CAPACITY;
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(c->d_in, buf, (size_t)len, cudaMemcpyHostToDevice, c->stream));
     const uint64_t cap = idx_capacity < c->d_out_cap ? idx_capacity : c->d_out_cap;
     c->slot = (c->slot + 1) % RESULT_SLOTS;
     c->last_flags = flags;
-    rc = enqueue(c, c->d_in, len, c->d_out, cap, flags, c->slot);
+    DocPlan d;
+    rc = plan_document(c, d, c->d_in, len, c->d_out, cap, flags, c->slot, nullptr);
     if (rc != SJB200_SUCCESS) return rc;
-    CK(cudaStreamSynchronize(c->stream));
-    const Stage1Result r = c->h_results[c->slot];
-    uint64_t ncopy = r.n_written < cap ? r.n_written : cap;
-    if (r.n_valid) ncopy = (uint64_t)r.n + 3;  // trailer included
-    if (ncopy) {
-        CK(cudaMemcpyAsync(idx_out, c->d_out, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+    // Streaming: the document goes to the device in chunks of whole tiles; chunk k is indexed by its own launch as soon
+    // as it has arrived (same generation: the look-back carries parity and cursor across launches), and its indexes
+    // travel back on a second stream while chunk k+1 is still being copied in -- both PCIe directions stay busy.
+    const uint64_t tile = (uint64_t)d.warps * 2048;
+    uint64_t tiles_per_chunk = c->chunk_bytes / tile;
+    if (tiles_per_chunk == 0) tiles_per_chunk = 1;
+    uint64_t nchunks = (d.p.ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (nchunks > (uint64_t)sjb200_ctx::MAX_CHUNKS) {
+        tiles_per_chunk = (d.p.ntiles + sjb200_ctx::MAX_CHUNKS - 1) / sjb200_ctx::MAX_CHUNKS;
+        nchunks = (d.p.ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
     }
+    for (uint64_t k = 0; k < nchunks; k++) {
+        const uint64_t t0 = k * tiles_per_chunk, t1 = (t0 + tiles_per_chunk < d.p.ntiles) ? t0 + tiles_per_chunk : d.p.ntiles;
+        const uint64_t b0 = t0 * tile, b1 = t1 * tile < len ? t1 * tile : len;
+        CK(cudaMemcpyAsync(c->d_in + b0, buf + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->stream));
+        c->h_progress[k] = 0;
+        rc = launch_range(c, d, (uint32_t)t0, (uint32_t)t1, c->d_progress + k, c->stream);
+        if (rc != SJB200_SUCCESS) return rc;
+        CK(cudaEventRecord(c->chunk_ev[k], c->stream));
+    }
+    uint64_t copied = 0;
+    for (uint64_t k = 0; k < nchunks; k++) {
+        CK(cudaEventSynchronize(c->chunk_ev[k]));
+        uint64_t have = *reinterpret_cast<volatile uint32_t *>(&c->h_progress[k]);  // indexes produced so far
+        if (k + 1 == nchunks) {
+            const Stage1Result r = c->h_results[c->slot];
+            have = r.n_valid ? (uint64_t)r.n + 3 : r.n_written;                      // the trailer travels with the last chunk
+        }
+        if (have > cap) have = cap;
+        if (have > copied) {
+            CK(cudaMemcpyAsync(idx_out + copied, c->d_out + copied, (size_t)(have - copied) * 4, cudaMemcpyDeviceToHost,
+                               c->copy_stream));
+            copied = have;
+        }
+    }
+    CK(cudaStreamSynchronize(c->copy_stream));
+    const Stage1Result r = c->h_results[c->slot];
     if (r.n_valid && n_out) *n_out = r.n;
     if (utf8_err_out) *utf8_err_out = (flags & SJB200_FLAG_NO_UTF8) ? -1 : r.utf8_error;
     return r.error;

@@ -78,8 +78,12 @@ struct Stage1Params {
     uint32_t *ticket;       // tile ticket counter, 0 at launch, reset by the last tile
     Stage1Result *result;
     int32_t *dev_status;    // optional device copy of {error, n} for on-device consumers (NCCL), may be null
-    uint32_t gen;           // generation of this call (1 .. 2^20-1)
-    uint32_t ntiles;
+    uint32_t gen;           // generation of this document (1 .. 2^20-1); all launches over one document share it
+    uint32_t ntiles;        // tiles of the whole document
+    uint32_t tile_begin;    // this launch covers tiles [tile_begin, tile_end): a document may be indexed in several
+    uint32_t tile_end;      //   launches (streaming host path); the look-back simply continues across them
+    uint32_t ticket_sel;    // which of the two alternating ticket counters this launch uses (persistent kernel)
+    uint32_t *progress;     // optional: indexes produced up to and including tile_end-1 (mapped host memory), may be null
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
     uint64_t *trace;        // debug builds (-DSJ_TRACE=1): 16 x u64 of timestamps per tile, else unused
 };
@@ -549,7 +553,7 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
 
     // ---- ticket + bulk load -------------------------------------------------------------------
     if (tid == 0) {
-        s_tile = atomicAdd(P.ticket, 1u);
+        s_tile = P.tile_begin + atomicAdd(P.ticket, 1u);
         mbar_init(bar, 1);
         fence_mbar_init();
     }
@@ -608,10 +612,11 @@ __global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_k
         if (lane == 0) {
             s_total = total;
             s_base = lb.base;
-            if (tile == (int)P.ntiles - 1) {
-                write_verdict(P, pre);
-                *P.ticket = 0;  // every tile has drawn its ticket by now
+            if (tile == (int)P.tile_end - 1) {
+                if (P.progress) *P.progress = pre.count;
+                *P.ticket = 0;  // every tile of this launch has drawn its ticket by now
             }
+            if (tile == (int)P.ntiles - 1) write_verdict(P, pre);
         }
     }
     __syncthreads();  // B: parity entering every warp and the output cursor are known

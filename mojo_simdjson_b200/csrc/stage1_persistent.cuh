@@ -73,16 +73,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
         }
         fence_mbar_init();
         // two ticket counters used alternately by successive launches: clear the one the NEXT launch will use
-        if (blockIdx.x == 0) P.ticket[(P.gen + 1) & 1u] = 0;
+        if (blockIdx.x == 0) P.ticket[(P.ticket_sel + 1) & 1u] = 0;
     }
     __syncthreads();
-    uint32_t *ticket = P.ticket + (P.gen & 1u);
+    uint32_t *ticket = P.ticket + (P.ticket_sel & 1u);
 
     // produce(it): one thread draws the ticket of iteration `it` and starts its bulk copy into the (free) input buffer;
     // when the tickets are exhausted it wakes the compute warps and the scan warp with "no more work"
     auto produce = [&](int it) {
-        const uint32_t k = atomicAdd(ticket, 1u);
-        if (k < P.ntiles) {
+        const uint32_t k = P.tile_begin + atomicAdd(ticket, 1u);
+        if (k < P.tile_end) {
             const int t = (int)k;
             s_tile_of = t;
             TRACE(P, t, 0, gtime());  // ticket drawn / copy issued
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                 st_desc(P.desc + cur, desc_pack_prefix(P.gen, pre));
                 S.s_in = s_in;
                 S.base = lb.base;
+                if (cur == (int)P.tile_end - 1 && P.progress) *P.progress = pre.count;
                 if (cur == (int)P.ntiles - 1) write_verdict(P, pre);
                 TRACE(P, cur, 4, gtime());  // look-back done
                 mbar_arrive(bar_carry + 8 * slot);  // release: S.s_in / S.base visible to the waiters

@@ -142,6 +142,35 @@ def test_validate_utf8_flag_through_facade():
         p.close()
 
 
+def test_host_path_streams_in_chunks(monkeypatch):
+    """sjb200_stage1 copies / indexes / copies back chunk by chunk (look-back state carried across launches)."""
+    from mojo_simdjson_b200 import synth
+    from mojo_simdjson_b200.dom_parser_implementation import DomParserImplementation
+
+    monkeypatch.setenv("SJB200_CHUNK_MIB", "1")
+    size = (20 << 20) + 12345
+    doc = synth.status_array(size)
+    p = DomParserImplementation(0, max_len=size)
+    try:
+        want = oracle.stage1(doc, impl="fast")
+        assert p.stage1(doc) == want.error == 0
+        assert p.n_structural_indexes == want.n
+        assert np.array_equal(p.structural_indexes[: want.n + 3], want.indexes)
+        # verdicts that need the whole document, decided in the last chunk
+        bad = doc.copy()
+        bad[size // 2] = 0x22  # a stray quote in the middle flips every string after it
+        want = oracle.stage1(bad, impl="fast")
+        p.n_structural_indexes = 777
+        assert p.stage1(bad) == want.error
+        assert want.error in (14, 15) and p.n_structural_indexes == 777
+        assert np.array_equal(p.structural_indexes[: want.n_written], want.indexes[: want.n_written])
+        ndj = synth.ndjson(3 << 20)
+        want = oracle.stage1(ndj, impl="fast")
+        assert p.stage1(ndj) == 0 and np.array_equal(p.structural_indexes[: want.n + 3], want.indexes)
+    finally:
+        p.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # config 5: adversarial set, device-resident path, every tile shape, aligned and misaligned input
 # ------------------------------------------------------------------------------------------------
@@ -217,6 +246,15 @@ def test_fuzz_nasty_device(dev, scratch, xs, mis):
 def test_fuzz_binary_device(dev, scratch, data, mis):
     res, out = run_device(dev, scratch, data, mis=mis, warps=2)
     assert_same(res, out, oracle.stage1(data))
+
+
+def test_alternating_kernel_kinds_and_tile_shapes(dev, scratch):
+    """Persistent launches alternate two ticket counters; launches of the other kernel in between must not disturb them."""
+    a = b'{"a":"' + b"x" * 3000 + b'","b":[1,2,3]}'
+    wa = oracle.stage1(a)
+    for warps in (2, 32, 2, 2, 32, 32, 2, 16, 4, 32, 8, 2, 24, 2):
+        res, out = run_device(dev, scratch, a, warps=warps)
+        assert_same(res, out, wa)
 
 
 def test_repeated_calls_reuse_descriptors(dev, scratch):
