@@ -276,27 +276,27 @@ def run_ours(args):
         ctx.set_warps(args.warps)
     torch.cuda.synchronize()
 
+    from mojo_simdjson_b200 import batch
+
+    driver = None
     if n_gpus == 1:
         seg_offsets = [0, size]
+        nseg = 1
     else:
-        seg_offsets = ctx.split(d_in, min(size, 0x7FFFFFFF))
-    nseg = len(seg_offsets) - 1
-    d_status = torch.zeros((nseg, 2), dtype=torch.int32, device=dev)
-    if world > 1:
-        d_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        d_counts_all = torch.zeros((world * nseg,), dtype=torch.int32, device=dev)
+        driver = batch.NdjsonBatchDriver(ctx, seg_bytes=min(size, 0x7FFFFFFF), max_segments=8)
+        seg_offsets = driver.plan(d_in)
+        nseg = len(seg_offsets) - 1
+    last_exchange = {}
 
     def step():
         if n_gpus == 1:
             rc = ctx.enqueue(d_in, d_out, flags)
+            if rc != errors.SUCCESS:
+                raise RuntimeError(f"launch failed: {errors.NAMES.get(rc, rc)}")
         else:
-            rc = ctx.run_segments_async(d_in, seg_offsets, d_out, d_status, flags)
-            # verdict exchange, enqueued behind the kernels with no host round trip
-            d_err.copy_(d_status[:, 0].max().reshape(1))
-            dist.all_reduce(d_err, op=dist.ReduceOp.MAX)
-            dist.all_gather_into_tensor(d_counts_all, d_status[:, 1].contiguous())
-        if rc != errors.SUCCESS:
-            raise RuntimeError(f"launch failed: {errors.NAMES.get(rc, rc)}")
+            # every segment's kernel, then the verdict exchange (all-reduce MAX of the error flag, all-gather of the
+            # per-segment counts), enqueued behind the kernels with no host round trip
+            last_exchange["worst"], last_exchange["counts"] = driver.enqueue(d_in, d_out, flags)
 
     # ---- correctness gate before any timing -------------------------------------------------------------
     if n_gpus == 1:
@@ -309,10 +309,11 @@ def run_ours(args):
     else:
         step()
         torch.cuda.synchronize()
-        st = d_status.cpu().numpy()
-        if int(d_err.item()) != 0:
-            raise RuntimeError(f"stage 1 failed on an NDJSON segment: {st.tolist()}")
-        n_total = int(st[:, 1].sum())
+        if int(last_exchange["worst"].item()) != 0:
+            raise RuntimeError(f"stage 1 failed on an NDJSON segment: {driver._status.cpu().tolist()}")
+        allc = last_exchange["counts"].cpu()
+        n_total = int(allc[rank][allc[rank] >= 0].sum())
+        assert allc.shape[0] == world
     density = n_total / size
 
     # ---- timed region: K passes, device-resident ----------------------------------------------------------
@@ -355,7 +356,7 @@ def run_ours(args):
         if n_gpus == 1:
             ctx.enqueue(d_in, d_out, flags)
         else:
-            ctx.run_segments_async(d_in, seg_offsets, d_out, d_status, flags)
+            ctx.run_segments_async(d_in, seg_offsets, d_out, driver._status, flags)
     kev1.record(stream)
     torch.cuda.synchronize()
     k_ms = kev0.elapsed_time(kev1) / kreps / nseg  # per kernel launch
@@ -364,7 +365,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic_bytes(), "peak_source": f"of {peak_kind}",
-                "kernel": "stage1_kernel", "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
+                "kernel": "stage1_persistent_kernel", "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
                 "structural_density": round(density, 4)}
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------
@@ -372,16 +373,19 @@ def run_ours(args):
     n_out = C.c_uint32(0)
     u8 = C.c_int32(0)
 
+    h_status = torch.zeros((nseg, 2), dtype=torch.int32)
+
     def e2e_step():
         worst = 0
         for s in range(nseg):
             a, b = seg_offsets[s], seg_offsets[s + 1]
             rc = L.sjb200_stage1(ctx._ctx, h_in.data_ptr() + a, b - a, h_out.data_ptr(), cap, C.byref(n_out), C.byref(u8), flags)
+            h_status[s, 0] = rc
+            h_status[s, 1] = n_out.value
             worst = max(worst, rc)
         if world > 1:
-            d_err.fill_(worst)
-            dist.all_reduce(d_err, op=dist.ReduceOp.MAX)
-            dist.all_gather_into_tensor(d_counts_all, d_status[:, 1].contiguous())
+            d_st = h_status.to(dev, non_blocking=True)
+            batch.exchange_verdicts(d_st[:, 0], d_st[:, 1], driver.max_segments)
         return worst
 
     e2e_step()
