@@ -10,6 +10,7 @@
 #include "../../include/simdjson_b200.h"
 #include "stage1_kernel.cuh"
 #include "stage1_persistent.cuh"
+#include "stage1_dataflow.cuh"
 
 using namespace sjb200;
 
@@ -51,6 +52,7 @@ struct sjb200_ctx {
     int kernel_kind = 1;                // 0: one tile per CTA, 1: persistent warp-specialised
     int sm_count = 0;
     int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
+    int flow_occ[3] = {0, 0, 0};           // same for the dataflow kernel, NC = 4, 8, 12
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -108,7 +110,30 @@ cudaError_t prepare_persist(int *occ) {
     if (*occ < 1) *occ = 1;
     return e;
 }
-bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24 || w == 32; }
+template <int NC, bool UTF8>
+cudaError_t launch_flow(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = FlowCfg<NC>;
+    const unsigned span = p.tile_end - p.tile_begin;
+    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
+    stage1_dataflow_kernel<NC, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+template <int NC>
+cudaError_t prepare_flow(int *occ) {
+    using Cfg = FlowCfg<NC>;
+    cudaError_t e = cudaFuncSetAttribute(stage1_dataflow_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stage1_dataflow_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(stage1_dataflow_kernel<NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_dataflow_kernel<NC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int a = 0, b = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_dataflow_kernel<NC, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_dataflow_kernel<NC, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    *occ = a < b ? a : b;
+    if (*occ < 1) *occ = 1;
+    return e;
+}
+bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32; }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (c->forced_warps) return c->forced_warps;
@@ -132,6 +157,7 @@ struct DocPlan {
     Stage1Params p;
     int warps;
     bool persist;
+    bool flow;
     bool utf8;
 };
 
@@ -162,10 +188,11 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     static int env_kind = -1;
     if (env_kind < 0) {
         const char *e = getenv("SJB200_KERNEL");
-        env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : 1) : 2;
+        env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : (strcmp(e, "flow") == 0 ? 3 : 1)) : 2;
     }
     const int kind = env_kind == 2 ? c->kernel_kind : env_kind;
-    d.persist = kind == 1 && d.warps <= 24;
+    d.flow = kind == 3 && (d.warps == 4 || d.warps == 8 || d.warps == 12);
+    d.persist = d.flow || (kind >= 1 && d.warps <= 24);
     const uint64_t tile = (uint64_t)d.warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
@@ -188,7 +215,14 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     const int warps = d.warps;
     const bool utf8 = d.utf8;
     cudaError_t e;
-    if (d.persist) {
+    if (d.flow) {
+        const int max_ctas = c->sm_count * c->flow_occ[warps == 12 ? 2 : (warps == 8 ? 1 : 0)];
+        switch (warps) {
+        case 12: e = utf8 ? launch_flow<12, true>(p, stream, max_ctas) : launch_flow<12, false>(p, stream, max_ctas); break;
+        case 8: e = utf8 ? launch_flow<8, true>(p, stream, max_ctas) : launch_flow<8, false>(p, stream, max_ctas); break;
+        default: e = utf8 ? launch_flow<4, true>(p, stream, max_ctas) : launch_flow<4, false>(p, stream, max_ctas); break;
+        }
+    } else if (d.persist) {
         const int idx = warps == 24 ? 4 : (warps == 16 ? 3 : (warps == 8 ? 2 : (warps == 4 ? 1 : 0)));
         const int max_ctas = c->sm_count * c->persist_occ[idx];
         switch (warps) {
@@ -320,6 +354,9 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_persist<8>(&c->persist_occ[2]);
     if (e == cudaSuccess) e = prepare_persist<16>(&c->persist_occ[3]);
     if (e == cudaSuccess) e = prepare_persist<24>(&c->persist_occ[4]);
+    if (e == cudaSuccess) e = prepare_flow<4>(&c->flow_occ[0]);
+    if (e == cudaSuccess) e = prepare_flow<8>(&c->flow_occ[1]);
+    if (e == cudaSuccess) e = prepare_flow<12>(&c->flow_occ[2]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {

@@ -35,6 +35,24 @@
 #ifndef SJ_PRODUCE_LATE
 #define SJ_PRODUCE_LATE 0
 #endif
+#ifndef SJ_FLOWREG8
+#define SJ_FLOWREG8 56
+#endif
+#ifndef SJ_REG8
+#define SJ_REG8 56
+#endif
+#ifndef SJ_REG16
+#define SJ_REG16 56
+#endif
+#ifndef SJ_REG24
+#define SJ_REG24 72
+#endif
+#ifndef SJ_SKIP_FLUSH
+#define SJ_SKIP_FLUSH 0
+#endif
+#ifndef SJ_SKIP_COMPUTE
+#define SJ_SKIP_COMPUTE 0
+#endif
 #ifndef SJ_TRACE
 #define SJ_TRACE 0
 #endif
@@ -438,7 +456,34 @@ __device__ __forceinline__ void write_verdict(const Stage1Params &P, const TileP
 // flatten one lane's structural bits (BitIndexer.write, :46-58) into dst[0..].  The words are bit-reversed so that one
 // FLO finds the lowest structural; per index: FLO (XU) + subtract (value) + shift + and-with-predicate + store.
 __device__ __forceinline__ void flatten_word(uint32_t *&dst, uint32_t bits, uint32_t v31) {
-#if SJ_LEAN_FLATTEN
+#if SJ_LEAN_FLATTEN == 2
+    // four indexes per trip: the clear-lowest-bit chain is cheap (IADD + LOP3), the four position searches (one FLO on
+    // the isolated bit each) are independent and overlap -- a warp issues in order, so one FLO per trip of a rolled
+    // loop would expose the full XU latency every iteration
+    const uint32_t v0 = v31 - 31u;
+    while (bits) {
+        const uint32_t t1 = bits & (bits - 1u), t2 = t1 & (t1 - 1u), t3 = t2 & (t2 - 1u);
+        const uint32_t p0 = 31u - (uint32_t)__clz((int)(bits & (0u - bits)));
+        const uint32_t p1 = 31u - (uint32_t)__clz((int)(t1 & (0u - t1)));
+        const uint32_t p2 = 31u - (uint32_t)__clz((int)(t2 & (0u - t2)));
+        const uint32_t p3 = 31u - (uint32_t)__clz((int)(t3 & (0u - t3)));
+        dst[0] = v0 + p0;
+        if (t1) dst[1] = v0 + p1;
+        if (t2) dst[2] = v0 + p2;
+        if (t3) dst[3] = v0 + p3;
+        dst += 1 + (t1 != 0) + (t2 != 0) + (t3 != 0);
+        bits = t3 & (t3 - 1u);
+    }
+#elif SJ_LEAN_FLATTEN == 3
+    // position of the lowest set bit = popc(bits ^ (bits - 1)) - 1: one XU op per index, no bit reversal, and the
+    // bits - 1 it needs is the same one that clears the bit
+    const uint32_t vm1 = v31 - 32u;
+    while (bits) {
+        const uint32_t t = bits - 1u;
+        *dst++ = vm1 + (uint32_t)__popc(bits ^ t);
+        bits &= t;
+    }
+#elif SJ_LEAN_FLATTEN
     uint32_t r = __brev(bits);
     while (r) {
         const uint32_t h = 31u - (uint32_t)__clz((int)r);  // FLO: highest set bit of the reversed word
@@ -453,8 +498,24 @@ __device__ __forceinline__ void flatten_word(uint32_t *&dst, uint32_t bits, uint
 #endif
 }
 __device__ __forceinline__ void flatten_to(uint32_t *dst, uint64_t structural, uint32_t v0) {
+#if SJ_LEAN_FLATTEN == 4
+    // both 32-bit words at once: two independent clear-lowest-bit chains per trip, half the trips (a warp issues in
+    // order, so the loop is bound by the latency of one trip, not by its instruction count)
+    uint32_t lo = (uint32_t)structural, hi = (uint32_t)(structural >> 32);
+    uint32_t *dhi = dst + __popc(lo);
+    const uint32_t vl = v0 - 1u, vh = v0 + 31u;
+    while (lo | hi) {
+        const uint32_t tl = lo - 1u, th = hi - 1u;
+        const uint32_t pl = (uint32_t)__popc(lo ^ tl), ph = (uint32_t)__popc(hi ^ th);
+        if (lo) *dst++ = vl + pl;
+        if (hi) *dhi++ = vh + ph;
+        lo = lo ? (lo & tl) : 0u;
+        hi = hi ? (hi & th) : 0u;
+    }
+#else
     flatten_word(dst, (uint32_t)structural, v0 + 31u);
     flatten_word(dst, (uint32_t)(structural >> 32), v0 + 63u);
+#endif
 }
 __device__ __forceinline__ void flatten_direct(uint32_t *out, uint64_t cap, uint64_t o, uint64_t structural, uint32_t v0) {
     uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));

@@ -32,7 +32,8 @@ struct PersistCfg {
     static constexpr int IN_BYTES = 16 + TILE;                 // halo + tile, single buffer
     static constexpr int STAGE_BYTES = NW * (WCAP + 4) * 4;
     static constexpr int SMEM_BYTES = ((IN_BYTES + 127) & ~127) + STAGE_BYTES;
-    static constexpr int MIN_CTAS = NW >= 24 ? 1 : (NW == 16 ? 2 : (NW == 8 ? 4 : (NW == 4 ? 6 : 8)));
+    // registers per thread: chosen so that SJ_OCCn CTAs of this shape are resident per SM (64 K registers / SM)
+    static constexpr int MAXREG = NW >= 24 ? SJ_REG24 : (NW == 16 ? SJ_REG16 : (NW == 8 ? SJ_REG8 : (NW == 4 ? 64 : 80)));
 };
 
 struct TileSlot {                 // double-buffered hand-off between compute warps and the scan warp
@@ -46,7 +47,7 @@ struct TileSlot {                 // double-buffered hand-off between compute wa
 };
 
 template <int NW, bool UTF8>
-__global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage1_persistent_kernel(const Stage1Params P) {
+__global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAXREG) stage1_persistent_kernel(const Stage1Params P) {
     using Cfg = PersistCfg<NW>;
     constexpr int TILE = Cfg::TILE;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -163,6 +164,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
             const uint32_t incl = warp_inclusive_sum(cnt);
             const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const uint64_t first = (uint64_t)S.base + (s_in ? S.off1[warp] : S.off0[warp]);  // the warp's first index
+#if SJ_SKIP_FLUSH
+            if (structural == 0x123456789ull) P.out[first] = wtotal;  // keep the values alive, write nothing
+            return;
+#endif
             if (wtotal <= (uint32_t)Cfg::WCAP) {
                 const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
                 flatten_to(stage + a + (incl - cnt), structural, old.v0);
@@ -204,7 +209,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, PersistCfg<NW>::MIN_CTAS) stage
                     }
                 }
 #endif
+#if SJ_SKIP_COMPUTE
+                // debug: pretend every 6th byte is structural, no classification at all
+                ph.m0 = 0x0410410410410410ull ^ in.w[0]; ph.m1 = ~ph.m0; ph.c0 = (uint32_t)__popcll(ph.m0); ph.c1 = 64 - ph.c0;
+                ph.v0 = (uint32_t)in.g0; ph.wc0 = __reduce_add_sync(0xFFFFFFFFu, ph.c0); ph.wc1 = __reduce_add_sync(0xFFFFFFFFu, ph.c1);
+                ph.wflags = 0; ph.tail = 0;
+#else
                 warp_compute<UTF8>(ph, in, lane, P);
+#endif
             }
             TileSlot &S = s_slot[slot];
             uint32_t order = 0;

@@ -29,12 +29,16 @@ def st(name, x):
 t0 = t[:, 0].min()
 print("kernel span us", (t[:, 13].max() - t0) / 1e3)
 st("ticket -> phase1 start (w0)", t[:, 1] - t[:, 0])
+per_cta = np.sort(t[:, 1])
+st("phase1 start w0 -> w-last", t[:, 7] - t[:, 1])
 st("input wait (w0)", t[:, 5])
 st("input wait (w-last)", t[:, 6])
 st("phase1 start w0 -> agg published", t[:, 2] - t[:, 1])
 st("ticket -> agg published", t[:, 2] - t[:, 0])
 st("agg published -> lookback start", t[:, 3] - t[:, 2])
 st("lookback duration", t[:, 4] - t[:, 3])
+st("ring-full wait (w0)", t[:, 14])
+st("ring-full wait (w-last)", t[:, 15])
 st("carry wait (w0)", t[:, 8])
 st("carry wait (w7)", t[:, 9])
 st("lookback done -> flush start (w0)", t[:, 10] - t[:, 4])
