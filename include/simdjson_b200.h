@@ -77,8 +77,29 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *ctx);
 
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
 int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
-/* Force the tile shape: warps per tile in {2,4,8,16,32} (2 KiB per warp), 0 = choose from the document size. */
+/* Force the tile shape: warps per tile in {2,4,8,12,16,24,32} (2 KiB per warp), 0 = choose from the document size. */
 int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
+/*
+ * Force the kernel organisation (tuning / test knob; every choice produces identical results):
+ *   AUTO        chosen from the document size (stream pipeline from 192 MiB on, persistent below)
+ *   TILE        one tile per CTA, look-back by warp 0
+ *   PERSISTENT  persistent CTAs, compute warps + scan warp, classify and flatten fused
+ *   DATAFLOW    persistent CTAs, classifier warps -> mask ring in shared memory -> flattener warps
+ *   SPLIT       two launches: classify (masks + per-chunk carries to HBM), then flatten; needs len/4 bytes of scratch,
+ *               allocated on first use (MEMALLOC if that fails)
+ *   STREAM      four launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp, two tiny
+ *               scan kernels over the chunk summaries, flatten; speculates that no backslash run covers a chunk's whole
+ *               32-byte look-behind and, when one does, re-runs the document with PERSISTENT (same results).  Scratch as
+ *               for SPLIT.  Whole documents only: the chunked host path uses PERSISTENT.
+ * A shape the chosen organisation does not support falls back to PERSISTENT / TILE for that call.
+ */
+#define SJB200_KERNEL_AUTO 0
+#define SJB200_KERNEL_TILE 1
+#define SJB200_KERNEL_PERSISTENT 2
+#define SJB200_KERNEL_DATAFLOW 3
+#define SJB200_KERNEL_SPLIT 4
+#define SJB200_KERNEL_STREAM 5
+int32_t sjb200_ctx_set_kernel(sjb200_ctx *ctx, int32_t kind);
 
 /*
  * Host-to-host drop-in for DomParserImplementation.stage1: copies buf to the device, indexes it, copies the

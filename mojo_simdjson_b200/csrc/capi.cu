@@ -11,6 +11,8 @@
 #include "stage1_kernel.cuh"
 #include "stage1_persistent.cuh"
 #include "stage1_dataflow.cuh"
+#include "stage1_split.cuh"
+#include "stage1_stream.cuh"
 
 using namespace sjb200;
 
@@ -18,6 +20,9 @@ namespace {
 
 constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
+// documents from this size on use the four-launch stream pipeline (its fixed cost, ~25 us of launch boundaries, is
+// recovered at ~150 MiB on a B200: 256 MiB 1372 vs 1278 GB/s, 64 MiB 935 vs 1096 GB/s)
+constexpr uint64_t SPLIT_MIN_BYTES = 192ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
@@ -49,10 +54,18 @@ struct sjb200_ctx {
     uint32_t slot = 0;                  // slot used by the most recent launch
     uint32_t gen = 0;
     int forced_warps = 0;
-    int kernel_kind = 1;                // 0: one tile per CTA, 1: persistent warp-specialised
+    int kernel_kind = SJB200_KERNEL_AUTO;  // sjb200_ctx_set_kernel
     int sm_count = 0;
     int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
     int flow_occ[3] = {0, 0, 0};           // same for the dataflow kernel, NC = 4, 8, 12
+    int split_occ[2] = {0, 0};             // same for the classify kernel of the split pair, NW = 8, 16
+    uint64_t *d_masks = nullptr;           // split pair: the two structural mask planes of every 2 KiB chunk
+    uint64_t *d_carry = nullptr;           //             one carry word per chunk
+    uint64_t split_chunks = 0;             //             chunks the two arrays hold (allocated on first use)
+    uint32_t *d_chunk_sum = nullptr;       // stream pipeline: per-chunk and per-1024-chunk summaries, speculation flag
+    uint32_t *d_block_sum = nullptr;
+    uint32_t *d_spec_flag = nullptr;
+    int stream_occ = 0;                    // resident CTAs per SM of the stream classify kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -133,6 +146,67 @@ cudaError_t prepare_flow(int *occ) {
     if (*occ < 1) *occ = 1;
     return e;
 }
+template <int NW, bool UTF8>
+cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = SplitCfg<NW>;
+    const unsigned span = p.tile_end - p.tile_begin;
+    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
+    stage1_classify_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    constexpr int FW = 8;
+    const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
+    stage1_flatten_kernel<FW><<<(c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s>>>(p, c0, c1);
+    return cudaGetLastError();
+}
+#ifndef SJ_STREAM_NW
+#define SJ_STREAM_NW 8
+#endif
+constexpr int STREAM_NW = SJ_STREAM_NW;
+template <bool UTF8>
+cudaError_t launch_stream(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = StreamCfg<STREAM_NW>;
+    const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
+    const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
+    const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
+    stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
+    const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
+    stage1_span_reduce_kernel<<<nblocks, 1024, 0, s>>>(p, nchunks);
+    stage1_span_carries_kernel<<<nblocks, 1024, 0, s>>>(p, nchunks);
+    constexpr int FW = 8;
+    stage1_flatten_kernel<FW><<<(nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s>>>(p, 0u, nchunks);
+    return cudaGetLastError();
+}
+cudaError_t prepare_stream(int *occ) {
+    using Cfg = StreamCfg<STREAM_NW>;
+    cudaError_t e = cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int a = 0, b = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_stream_classify_kernel<STREAM_NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    *occ = a < b ? a : b;
+    if (*occ < 1) *occ = 1;
+    return e;
+}
+template <int NW>
+cudaError_t prepare_split(int *occ) {
+    using Cfg = SplitCfg<NW>;
+    cudaError_t e = cudaFuncSetAttribute(stage1_classify_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(stage1_classify_kernel<NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_flatten_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int a = 0, b = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_classify_kernel<NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
+    *occ = a < b ? a : b;
+    if (*occ < 1) *occ = 1;
+    return e;
+}
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32; }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
@@ -158,8 +232,21 @@ struct DocPlan {
     int warps;
     bool persist;
     bool flow;
+    bool split;
+    bool stream;
     bool utf8;
 };
+
+void free_split_scratch(sjb200_ctx *c) {
+    cudaFree(c->d_masks);
+    cudaFree(c->d_carry);
+    cudaFree(c->d_chunk_sum);
+    cudaFree(c->d_block_sum);
+    cudaFree(c->d_spec_flag);
+    c->d_masks = c->d_carry = nullptr;
+    c->d_chunk_sum = c->d_block_sum = c->d_spec_flag = nullptr;
+    c->split_chunks = 0;
+}
 
 int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap,
                       uint32_t flags, uint32_t slot, int32_t *d_status) {
@@ -180,6 +267,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     if (c->gen == 0) {  // the 20-bit generation wrapped: clear descriptors and tickets once (stream ordered), restart at 1
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
         cudaMemsetAsync(c->ticket, 0, 256, c->stream);
+        if (c->d_spec_flag) cudaMemsetAsync(c->d_spec_flag, 0, 256, c->stream);
         c->gen = 1;
     }
     p.gen = c->gen;
@@ -188,11 +276,20 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     static int env_kind = -1;
     if (env_kind < 0) {
         const char *e = getenv("SJB200_KERNEL");
-        env_kind = e ? (strcmp(e, "tile") == 0 ? 0 : (strcmp(e, "flow") == 0 ? 3 : 1)) : 2;
+        env_kind = SJB200_KERNEL_AUTO;
+        if (e && strcmp(e, "tile") == 0) env_kind = SJB200_KERNEL_TILE;
+        if (e && strcmp(e, "persist") == 0) env_kind = SJB200_KERNEL_PERSISTENT;
+        if (e && strcmp(e, "flow") == 0) env_kind = SJB200_KERNEL_DATAFLOW;
+        if (e && strcmp(e, "split") == 0) env_kind = SJB200_KERNEL_SPLIT;
+        if (e && strcmp(e, "stream") == 0) env_kind = SJB200_KERNEL_STREAM;
     }
-    const int kind = env_kind == 2 ? c->kernel_kind : env_kind;
-    d.flow = kind == 3 && (d.warps == 4 || d.warps == 8 || d.warps == 12);
-    d.persist = d.flow || (kind >= 1 && d.warps <= 24);
+    int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : env_kind;
+    if (kind == SJB200_KERNEL_AUTO) kind = p.alen >= SPLIT_MIN_BYTES ? SJB200_KERNEL_STREAM : SJB200_KERNEL_PERSISTENT;
+    d.stream = kind == SJB200_KERNEL_STREAM;
+    if (d.stream && d.warps > 24) d.warps = 16;   // shape of the fallback (persistent) launch
+    d.split = kind == SJB200_KERNEL_SPLIT && (d.warps == 8 || d.warps == 16);
+    d.flow = kind == SJB200_KERNEL_DATAFLOW && (d.warps == 4 || d.warps == 8 || d.warps == 12);
+    d.persist = d.stream || d.split || d.flow || (kind != SJB200_KERNEL_TILE && d.warps <= 24);
     const uint64_t tile = (uint64_t)d.warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
@@ -202,6 +299,35 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     // ticket counters: [0],[1] alternate between successive persistent launches, [2] serves the one-tile-per-CTA kernel
     p.ticket = d.persist ? c->ticket : c->ticket + 2;
     d.utf8 = !(flags & SJB200_FLAG_NO_UTF8);
+    p.masks = nullptr;
+    p.carry = nullptr;
+    p.chunk_sum = nullptr;
+    p.block_sum = nullptr;
+    p.spec_flag = nullptr;
+    if (d.split || d.stream) {
+        const uint64_t chunks = ntiles * (uint64_t)d.warps;
+        if (chunks > c->split_chunks) {  // first use (or a larger document than before): (re)allocate, stream ordered
+            cudaStreamSynchronize(c->stream);
+            free_split_scratch(c);
+            const uint64_t want = (c->max_len + 16) / 2048 + 64;
+            const uint64_t n = chunks > want ? chunks : want;
+            if (cudaMalloc(&c->d_masks, n * 512) != cudaSuccess || cudaMalloc(&c->d_carry, n * 8) != cudaSuccess ||
+                cudaMalloc(&c->d_chunk_sum, n * 16) != cudaSuccess || cudaMalloc(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16) != cudaSuccess ||
+                cudaMalloc(&c->d_spec_flag, 256) != cudaSuccess || cudaMemset(c->d_spec_flag, 0, 256) != cudaSuccess) {
+                free_split_scratch(c);
+                cudaGetLastError();
+                return SJB200_MEMALLOC;
+            }
+            c->split_chunks = n;
+        }
+        p.masks = c->d_masks;
+        p.carry = c->d_carry;
+        if (d.stream) {
+            p.chunk_sum = c->d_chunk_sum;
+            p.block_sum = c->d_block_sum;
+            p.spec_flag = c->d_spec_flag;
+        }
+    }
     return SJB200_SUCCESS;
 }
 
@@ -215,7 +341,21 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     const int warps = d.warps;
     const bool utf8 = d.utf8;
     cudaError_t e;
-    if (d.flow) {
+    const bool whole = tile_begin == 0 && tile_end == d.p.ntiles;
+    if (!(d.stream && whole)) p.spec_flag = nullptr;   // a partial range is indexed by the persistent kernel alone
+    if (d.stream && whole) {
+        // speculative pipeline, then the persistent kernel as its exact fallback (returns at once unless the flag was raised)
+        e = utf8 ? launch_stream<true>(p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(p, stream, c->sm_count * c->stream_occ);
+        c->launches += 4;
+    }
+    if (d.stream && whole && e != cudaSuccess) {
+        return cuda_err(e);
+    } else if (d.split) {
+        const int max_ctas = c->sm_count * c->split_occ[warps == 16 ? 1 : 0];
+        if (warps == 16) e = utf8 ? launch_split<16, true>(p, stream, max_ctas) : launch_split<16, false>(p, stream, max_ctas);
+        else e = utf8 ? launch_split<8, true>(p, stream, max_ctas) : launch_split<8, false>(p, stream, max_ctas);
+        c->launches++;
+    } else if (d.flow && !d.stream) {
         const int max_ctas = c->sm_count * c->flow_occ[warps == 12 ? 2 : (warps == 8 ? 1 : 0)];
         switch (warps) {
         case 12: e = utf8 ? launch_flow<12, true>(p, stream, max_ctas) : launch_flow<12, false>(p, stream, max_ctas); break;
@@ -357,6 +497,9 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_flow<4>(&c->flow_occ[0]);
     if (e == cudaSuccess) e = prepare_flow<8>(&c->flow_occ[1]);
     if (e == cudaSuccess) e = prepare_flow<12>(&c->flow_occ[2]);
+    if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
+    if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
+    if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -379,6 +522,7 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     cudaFree(c->ticket);
     cudaFree(c->d_split);
     cudaFree(c->d_trace);
+    free_split_scratch(c);
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_progress) cudaFreeHost(c->h_progress);
     for (int k = 0; k < sjb200_ctx::MAX_CHUNKS; k++)
@@ -397,6 +541,13 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *c, void *cuda_stream) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     c->own_stream = false;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_set_kernel(sjb200_ctx *c, int32_t kind) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (kind < SJB200_KERNEL_AUTO || kind > SJB200_KERNEL_STREAM) return SJB200_UNEXPECTED_ERROR;
+    c->kernel_kind = kind;
     return SJB200_SUCCESS;
 }
 

@@ -171,8 +171,8 @@ struct Utf8Pre32 {
     uint32_t p5, p4;
 };
 
-template <bool UTF8>
-SJ_HD void classify32(const uint32_t p[8], Classes32 &c, Utf8Pre32 &u8) {
+// the JSON classes of 32 bytes (reference json_character_block.mojo / haswell.mojo:44-69, as nibble conditions on planes)
+SJ_HD void classify_json32(const uint32_t p[8], Classes32 &c) {
     const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4], p5 = p[5], p6 = p[6], p7 = p[7];
     const uint32_t u = ~p7 & ~p6;         // 00xx xxxx
     const uint32_t v = ~p7 & p6;          // 01xx xxxx
@@ -191,22 +191,31 @@ SJ_HD void classify32(const uint32_t p[8], Classes32 &c, Utf8Pre32 &u8) {
     c.bs = h5 & loC;
     c.op = (k1 & loC) | (k2 & loA) | (k3 & (loB | loD));
     c.ctl = u & ~p5;
-    if (UTF8) {
-        const uint32_t A = p7 & p6, B = A & p5, C = B & p4;
-        const uint32_t L3 = B & ~p4;
-        const uint32_t lo4 = ~p3 & p2 & ~p1 & ~p0;
-        u8.hi = p7;
-        u8.cont = p7 & ~p6;
-        u8.A = A;
-        u8.B = B;
-        u8.C = C;
-        u8.bad = (A & ~p5 & ~p4 & ~p3 & ~p2 & ~p1) | (C & (p3 | (p2 & (p1 | p0))));
-        u8.U = B & lo0;                    // E0, F0 (also F8..: already bad)
-        u8.V = (L3 & loD) | (C & lo4);     // ED, F4
-        u8.W = C & (lo0 | lo4);            // F0, F4
-        u8.p5 = p5;
-        u8.p4 = p4;
-    }
+}
+// the UTF-8 lead / continuation classes of the same 32 bytes; only needed when some byte is >= 0x80
+SJ_HD void utf8_pre32(const uint32_t p[8], Utf8Pre32 &u8) {
+    const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4], p5 = p[5], p6 = p[6], p7 = p[7];
+    const uint32_t A = p7 & p6, B = A & p5, C = B & p4;
+    const uint32_t L3 = B & ~p4;
+    const uint32_t q = ~p3 & ~p1 & ~p0;   // low nibble 0 or 4
+    const uint32_t lo0 = q & ~p2, lo4 = q & p2;
+    const uint32_t loD = p3 & p2 & ~p1 & p0;
+    u8.hi = p7;
+    u8.cont = p7 & ~p6;
+    u8.A = A;
+    u8.B = B;
+    u8.C = C;
+    u8.bad = (A & ~p5 & ~p4 & ~p3 & ~p2 & ~p1) | (C & (p3 | (p2 & (p1 | p0))));
+    u8.U = B & lo0;                    // E0, F0 (also F8..: already bad)
+    u8.V = (L3 & loD) | (C & lo4);     // ED, F4
+    u8.W = C & q;                      // F0, F4
+    u8.p5 = p5;
+    u8.p4 = p4;
+}
+template <bool UTF8>
+SJ_HD void classify32(const uint32_t p[8], Classes32 &c, Utf8Pre32 &u8) {
+    classify_json32(p, c);
+    if (UTF8) utf8_pre32(p, u8);
 }
 
 SJ_HD uint64_t join64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }

@@ -103,6 +103,12 @@ struct Stage1Params {
     uint32_t ticket_sel;    // which of the two alternating ticket counters this launch uses (persistent kernel)
     uint32_t *progress;     // optional: indexes produced up to and including tile_end-1 (mapped host memory), may be null
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
+    uint64_t *masks;        // split pair only: [chunk][parity][lane] structural masks, 512 bytes per 2 KiB chunk
+    uint64_t *carry;        // split pair only: per chunk, bit 63 = starts inside a string, bits 0..39 = rank of its first index
+    uint32_t *chunk_sum;    // stream pipeline only: 16 bytes per chunk {count0, count1, flags, 0}
+    uint32_t *block_sum;    // stream pipeline only: the same per 1024 chunks
+    uint32_t *spec_flag;    // stream pipeline: == gen once a chunk could not resolve its escape carry locally.  Persistent
+                            // kernel: if non-null, run only when *spec_flag == gen (it is the exact fallback)
     uint64_t *trace;        // debug builds (-DSJ_TRACE=1): 16 x u64 of timestamps per tile, else unused
 };
 
@@ -347,18 +353,21 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
         bitplanes32(in.w, pl);
         bitplanes32(in.w + 8, ph);
         Classes32 cl, ch;
-        Utf8Pre32 ul, uh;
-        classify32<UTF8>(pl, cl, ul);
-        classify32<UTF8>(ph, ch, uh);
+        classify_json32(pl, cl);
+        classify_json32(ph, ch);
         m.bs = join64(cl.bs, ch.bs);
         m.rq = join64(cl.rq, ch.rq);
         m.op = join64(cl.op, ch.op);
         m.ws = join64(cl.ws, ch.ws);
         m.ctl = join64(cl.ctl, ch.ctl);
         if (UTF8) {
-            // whole-warp fast path: nothing >= 0x80 in these 2 KiB nor in the 4 bytes before each chunk
-            const bool any_hi = ((ul.hi | uh.hi) != 0) || ((in.prev & 0x80808080u) != 0);
+            // whole-warp fast path: nothing >= 0x80 in these 2 KiB nor in the 4 bytes before each lane's 64 (the lead /
+            // continuation classes are not even computed then)
+            const bool any_hi = ((pl[7] | ph[7]) != 0) || ((in.prev & 0x80808080u) != 0);
             if (__any_sync(0xFFFFFFFFu, any_hi)) {
+                Utf8Pre32 ul, uh;
+                utf8_pre32(pl, ul);
+                utf8_pre32(ph, uh);
                 const Utf8Carry uc = utf8_carry_from_prev_word(in.prev);
                 uint32_t tail_must;
                 const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);

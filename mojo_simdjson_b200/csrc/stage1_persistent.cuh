@@ -60,6 +60,12 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
     __shared__ uint32_t s_loaded;               // compute warps that have pulled the current tile into registers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (P.spec_flag && __ldg(P.spec_flag) != P.gen) {
+        // launched as the exact fallback of the stream pipeline (stage1_stream.cuh) and not needed: only keep the
+        // ticket-counter alternation intact
+        if (blockIdx.x == 0 && tid == 0) P.ticket[(P.ticket_sel + 1) & 1u] = 0;
+        return;
+    }
     const uint32_t bar_in_full = smem_u32(&s_bar[0]), bar_in_empty = smem_u32(&s_bar[1]);
     const uint32_t bar_sum = smem_u32(&s_bar[2]), bar_carry = smem_u32(&s_bar[2 + NS]);  // + 8 * slot
 

@@ -1,0 +1,249 @@
+// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of four stream-ordered launches with no
+// waiting between warps, CTAs or launches other than stream order:
+//
+//   stream_classify : every warp is its own pipeline.  Warp g handles the 2 KiB chunks g, g + G, g + 2G, ... (G = warps in
+//                     the grid), each fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
+//                     mbarrier each) together with the 32 bytes before it, which decide the escape / scalar carries
+//                     entering the chunk.  Output per chunk: the two structural mask planes (string state entering the
+//                     chunk unknown -> one plane per parity) and a 16-byte summary {count0, count1, flags}.
+//   span_reduce     : 1024 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
+//   span_carries    : block prefix from the block aggregates, then the same local scan -> one carry word per chunk
+//                     (bit 63 = starts inside a string, bits 0..39 = rank of its first index) and the verdict.
+//   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
+//
+// The only carry stage 1 cannot resolve from a bounded look-behind is the escape state after a backslash run that covers
+// the whole 32-byte look-behind of a chunk.  A chunk that sees one raises `spec_flag` (stores the document generation);
+// the three later launches then do nothing and the persistent kernel, enqueued behind them with Stage1Params::spec_flag
+// set, redoes the document exactly.  Otherwise that kernel returns at once.  Results are identical either way.
+// Reference: json_structural_indexer.mojo:83-186 (step / next / finish), restated in oracle/stage1_oracle.c.
+#pragma once
+#include "stage1_split.cuh"
+
+#ifndef SJ_STREAMREG
+#define SJ_STREAMREG 56
+#endif
+#ifndef SJ_STREAM_DEPTH
+#define SJ_STREAM_DEPTH 3
+#endif
+
+namespace sjb200 {
+
+#if defined(__CUDACC__)
+
+template <int NW>
+struct StreamCfg {
+    static constexpr int THREADS = NW * 32;
+    static constexpr int DEPTH = SJ_STREAM_DEPTH;
+    static constexpr int HALO = 32;
+    static constexpr int BUF = 2048 + HALO;                 // 16-byte multiple
+    static constexpr int SMEM_BYTES = NW * DEPTH * BUF;
+    static constexpr int MAXREG = SJ_STREAMREG;
+};
+
+// phase 1 input of one lane from the warp's private buffer; `chunk` points at the chunk's first byte, HALO bytes before it
+// are the preceding input (chunk > 0)
+template <bool UTF8>
+__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, const Stage1Params &P,
+                                           uint32_t &unresolved) {
+    const int64_t alen = (int64_t)P.alen;
+    const int64_t cb = (int64_t)c * 2048;
+    in.g0 = cb + lane * 64;
+    const bool edge = (c == 0) || (cb + 2048 > alen);
+    const uint4 *src = reinterpret_cast<const uint4 *>(chunk + lane * 64);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint4 v = src[q];
+        in.w[4 * q + 0] = v.x;
+        in.w[4 * q + 1] = v.y;
+        in.w[4 * q + 2] = v.z;
+        in.w[4 * q + 3] = v.w;
+    }
+    in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(chunk + lane * 64 - 4) : 0u;
+    if (edge) {  // first / last chunk: bytes outside [mis, alen) read as 0x20 (reference tail padding)
+#pragma unroll
+        for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
+        if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
+    }
+    PrevState st = {0, 0, 0};
+    if (c > 0) {  // 32 bytes of look-behind, all inside the document (c >= 1, mis < 16)
+        const uint32_t b = (uint32_t)chunk[-1 - lane];
+        const uint32_t bsm = __ballot_sync(0xFFFFFFFFu, b == 0x5Cu);
+        const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, b, 0);
+        st = prev_state(bsm, 32, c1);
+    }
+    unresolved = st.unresolved;
+    in.wst = st;
+}
+
+template <int NW, bool UTF8>
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks) {
+    using Cfg = StreamCfg<NW>;
+    constexpr int DEPTH = Cfg::DEPTH;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *bufs = smem_raw + warp * (DEPTH * Cfg::BUF);
+    const uint32_t bar0 = smem_u32(&s_bar[warp * DEPTH]);
+    const uint32_t gw = blockIdx.x * NW + warp, stride = gridDim.x * NW;
+
+    auto fetch = [&](uint32_t c, int b) {  // lane 0: start the bulk copy of chunk c (+ look-behind) into buffer b
+        const int64_t cb = (int64_t)c * 2048;
+        int64_t nbytes = (int64_t)P.alen - cb;
+        nbytes = nbytes > 2048 ? 2048 : nbytes;
+        nbytes = (nbytes + 15) & ~15ll;                      // stays inside the last 16-byte line of the data
+        const uint32_t halo = c > 0 ? (uint32_t)Cfg::HALO : 0u;
+        mbar_expect_tx(bar0 + 8 * b, (uint32_t)nbytes + halo);
+        bulk_load(smem_u32(bufs) + b * Cfg::BUF + Cfg::HALO - halo, P.abase + cb - halo, (uint32_t)nbytes + halo, bar0 + 8 * b);
+    };
+    if (lane == 0) {
+        for (int b = 0; b < DEPTH; b++) mbar_init(bar0 + 8 * b, 1);
+        fence_mbar_init();
+        for (int b = 0; b < DEPTH; b++) {
+            const uint64_t c = (uint64_t)gw + (uint64_t)b * stride;
+            if (c < nchunks) fetch((uint32_t)c, b);
+        }
+    }
+    __syncwarp();
+    uint32_t k = 0;
+    int b = 0;
+    uint32_t phase = 0;
+    for (uint64_t c64 = gw; c64 < nchunks; c64 += stride, k++) {
+        const uint32_t c = (uint32_t)c64;
+        mbar_wait(bar0 + 8 * b, phase);
+        LanePhase1 ph;
+        {
+            LaneInput in;
+            uint32_t unresolved;
+            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, P, unresolved);
+            __syncwarp();  // every lane has its bytes in registers: the buffer can be refilled
+            if (lane == 0) {
+                const uint64_t cn = c64 + (uint64_t)DEPTH * stride;
+                if (cn < nchunks) fetch((uint32_t)cn, b);
+                if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
+            }
+            warp_compute<UTF8>(ph, in, lane, P);
+        }
+        uint64_t *mp = P.masks + (size_t)c * 64 + lane;
+        __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
+        __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
+        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
+        if (++b == DEPTH) {
+            b = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered scan of chunk summaries (1024 per CTA, one per thread)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ SpanAcc span_from_summary(const uint4 s) {
+    SpanAcc a;
+    a.par = s.z & 1u;
+    a.c[0] = s.x;
+    a.c[1] = s.y;
+    a.un[0] = (s.z >> 1) & 1u;
+    a.un[1] = (s.z >> 2) & 1u;
+    a.u8 = (s.z >> 3) & 1u;
+    return a;
+}
+__device__ __forceinline__ uint32_t span_flags(const SpanAcc &a) { return (a.par & 1u) | (a.un[0] << 1) | (a.un[1] << 2) | (a.u8 << 3); }
+__device__ __forceinline__ SpanAcc span_shfl_up(const SpanAcc &a, int d) {
+    SpanAcc r;
+    r.c[0] = __shfl_up_sync(0xFFFFFFFFu, a.c[0], d);
+    r.c[1] = __shfl_up_sync(0xFFFFFFFFu, a.c[1], d);
+    const uint32_t f = __shfl_up_sync(0xFFFFFFFFu, span_flags(a), d);
+    r.par = f & 1u;
+    r.un[0] = (f >> 1) & 1u;
+    r.un[1] = (f >> 2) & 1u;
+    r.u8 = (f >> 3) & 1u;
+    return r;
+}
+__device__ __forceinline__ SpanAcc warp_span_inclusive(SpanAcc a, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SpanAcc o = span_shfl_up(a, d);
+        if (lane >= d) a = span_concat(o, a);
+    }
+    return a;
+}
+// inclusive scan over the CTA's 1024 threads in thread order; returns this thread's inclusive span, `total` = the CTA's
+__device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint4 *s_w /* [32] */, SpanAcc &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SpanAcc a = warp_span_inclusive(mine, lane);
+    if (lane == 31) s_w[warp] = make_uint4(a.c[0], a.c[1], span_flags(a), 0u);
+    __syncthreads();
+    if (warp == 0) {
+        SpanAcc w = warp_span_inclusive(span_from_summary(s_w[lane]), lane);
+        __syncwarp();
+        s_w[lane] = make_uint4(w.c[0], w.c[1], span_flags(w), 0u);   // inclusive over warps
+    }
+    __syncthreads();
+    total = span_from_summary(s_w[31]);
+    if (warp > 0) a = span_concat(span_from_summary(s_w[warp - 1]), a);
+    __syncthreads();   // s_w may be reused by the caller
+    return a;
+}
+
+constexpr int SPAN_PER_THREAD = 4;                         // consecutive chunk summaries per thread
+constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
+
+__global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks) {
+    __shared__ uint4 s_w[32];
+    if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
+    const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
+    SpanAcc mine = span_empty();
+#pragma unroll
+    for (int k = 0; k < SPAN_PER_THREAD; k++)
+        if (c0 + k < nchunks) mine = span_concat(mine, span_from_summary(reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k]));
+    SpanAcc total;
+    block_span_inclusive(mine, s_w, total);
+    if (threadIdx.x == 0) reinterpret_cast<uint4 *>(P.block_sum)[blockIdx.x] = make_uint4(total.c[0], total.c[1], span_flags(total), 0u);
+}
+
+__global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1Params P, uint32_t nchunks) {
+    __shared__ uint4 s_w[32];
+    if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
+    const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
+    uint4 sum[SPAN_PER_THREAD];
+    SpanAcc mine = span_empty();
+#pragma unroll
+    for (int k = 0; k < SPAN_PER_THREAD; k++) {
+        sum[k] = c0 + k < nchunks ? reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k] : make_uint4(0u, 0u, 0u, 0u);
+        mine = span_concat(mine, span_from_summary(sum[k]));
+    }
+    // everything before this block: ordered reduction of the block aggregates 0 .. blockIdx.x-1
+    SpanAcc before = span_empty();
+    for (uint32_t b0 = 0; b0 < blockIdx.x; b0 += 1024u) {
+        const uint32_t j = b0 + threadIdx.x;
+        const SpanAcc bj = j < blockIdx.x ? span_from_summary(reinterpret_cast<const uint4 *>(P.block_sum)[j]) : span_empty();
+        SpanAcc total;
+        block_span_inclusive(bj, s_w, total);
+        before = span_concat(before, total);
+    }
+    SpanAcc total;
+    const SpanAcc incl = span_concat(before, block_span_inclusive(mine, s_w, total));
+    // the document starts outside a string: the state entering a chunk is the span before it evaluated at s = 0.
+    // Walk this thread's chunks backwards from its inclusive span: before(k) = inclusive(k) "minus" chunk k.
+    uint32_t par = incl.par & 1u, cnt = incl.c[0], un = incl.un[0], u8 = incl.u8;
+    if (c0 < nchunks && c0 + SPAN_PER_THREAD >= nchunks) {   // this thread owns the last chunk: the verdict
+        TilePrefix pre;
+        pre.s_out = par;
+        pre.e_out = 0;
+        pre.p_out = 0;
+        pre.err = (un ? EF_UNESCAPED : 0u) | (u8 ? EF_UTF8 : 0u);
+        pre.count = cnt;
+        write_verdict(P, pre);
+    }
+#pragma unroll
+    for (int k = SPAN_PER_THREAD - 1; k >= 0; k--) {
+        const uint32_t s_in = (par ^ sum[k].z) & 1u;               // parity before chunk k
+        cnt -= s_in ? sum[k].y : sum[k].x;                          // rank of its first index
+        par = s_in;
+        if (c0 + k < nchunks) P.carry[c0 + k] = (uint64_t)cnt | (s_in ? CARRY_INSIDE : 0ull);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sjb200

@@ -44,7 +44,15 @@ class Stage1Context:
     def set_warps(self, warps: int) -> None:
         rc = self._lib.sjb200_ctx_set_warps(self._ctx, warps)
         if rc != errors.SUCCESS:
-            raise ValueError("warps must be 0, 2, 4, 8, 16 or 32")
+            raise ValueError("warps must be 0, 2, 4, 8, 12, 16, 24 or 32")
+
+    KERNELS = {"auto": 0, "tile": 1, "persistent": 2, "dataflow": 3, "split": 4, "stream": 5}
+
+    def set_kernel(self, kind) -> None:
+        """Force the kernel organisation (include/simdjson_b200.h, SJB200_KERNEL_*); results do not depend on it."""
+        rc = self._lib.sjb200_ctx_set_kernel(self._ctx, self.KERNELS[kind] if isinstance(kind, str) else int(kind))
+        if rc != errors.SUCCESS:
+            raise ValueError(f"unknown kernel kind {kind!r}")
 
     def close(self):
         if self._ctx:

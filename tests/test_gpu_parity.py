@@ -58,13 +58,15 @@ def scratch():
     return Scratch(4 << 20)
 
 
-def run_device(dev, scratch, data: bytes, mis=0, flags=0, warps=0, cap=None):
+def run_device(dev, scratch, data: bytes, mis=0, flags=0, warps=0, cap=None, kernel="auto"):
     dev.set_warps(warps)
+    dev.set_kernel(kernel)
     view = scratch.put(data, mis)
     out = scratch.out if cap is None else scratch.out[:cap]
     scratch.out[: len(data) + 8].fill_(-1)
     res = dev.index(view, out, flags)
     dev.set_warps(0)
+    dev.set_kernel("auto")
     return res, scratch.out
 
 
@@ -192,6 +194,71 @@ def test_adversarial_corpus_device(dev, scratch, warps):
                 raise AssertionError(f"case {name} mis={mis} warps={warps}") from e
 
 
+@pytest.mark.parametrize("kernel,warps", [("tile", 8), ("persistent", 8), ("persistent", 24), ("dataflow", 4), ("dataflow", 8),
+                                          ("dataflow", 12), ("split", 8), ("split", 16), ("stream", 8), ("stream", 2)])
+def test_adversarial_corpus_every_kernel_organisation(dev, scratch, kernel, warps):
+    """The same corpus through each kernel organisation (sjb200_ctx_set_kernel): results must not depend on it."""
+    tiles = tuple(sorted({warps * 2048, 4096}))
+    corpus = cases.adversarial_cases(tile_bytes=tiles)[::2]
+    for k, (name, data) in enumerate(corpus):
+        if not data:
+            continue
+        want = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+        for mis in ((0, 11) if k % 4 == 0 else (0,)):
+            res, out = run_device(dev, scratch, data, mis=mis, warps=warps, kernel=kernel)
+            try:
+                assert_same(res, out, want)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"case {name} mis={mis} warps={warps} kernel={kernel}") from e
+
+
+def test_stream_pipeline_speculation_and_fallback(dev, scratch):
+    """The stream pipeline gives up when a backslash run covers the 32 bytes before a 2 KiB chunk; the persistent kernel
+    behind it must then produce the document (and must stay out of the way otherwise)."""
+    for run in (0, 1, 30, 31, 32, 33, 64, 65, 2047, 2048, 2049, 5000):
+        for pad in (2048 - 2, 2048 - 1, 2048, 4096 - 33, 4096 - 1):
+            head = b'["' + b"a" * (pad - 2 - run) if pad - 2 - run >= 0 else b'["'
+            data = head + b"\\" * 0 + b"\\"[:1] * run + b'"x", "y\\"", 1, {"k": "\\\\"}]' + b" " * 3000 + b"[]"
+            want = oracle.stage1(data, impl="ref")
+            for kernel in ("stream", "persistent"):
+                res, out = run_device(dev, scratch, data, kernel=kernel, warps=8)
+                try:
+                    assert_same(res, out, want)
+                except AssertionError as e:  # pragma: no cover
+                    raise AssertionError(f"run={run} pad={pad} kernel={kernel}") from e
+    # alternate documents that do / do not trigger the fallback: no state may leak between calls
+    ok = b'{"a": [1, 2, 3], "b": "' + b"z" * 9000 + b'"}'
+    bad = b'["' + b"a" * 2040 + b"\\"[:1] * 200 + b'" ]'
+    wok, wbad = oracle.stage1(ok), oracle.stage1(bad)
+    for _ in range(6):
+        res, out = run_device(dev, scratch, ok, kernel="stream")
+        assert_same(res, out, wok)
+        res, out = run_device(dev, scratch, bad, kernel="stream")
+        assert_same(res, out, wbad)
+
+
+def test_split_pair_capacity_and_flags(dev, scratch):
+    data = b'[' + b'1,' * 40000 + b'1]'
+    want = oracle.stage1(data, impl="fast")
+    for cap in (want.n + 3, want.n + 2, want.n, 1000, 3):
+        res, out = run_device(dev, scratch, data, cap=cap, warps=8, kernel="split")
+        if cap >= want.n + 3:
+            assert_same(res, out, want)
+        else:
+            assert res.error == 1 and res.n is None, cap
+            keep = min(cap, want.n)
+            assert np.array_equal(out[:keep].cpu().numpy().view(np.uint32), want.indexes[:keep]), cap
+            assert int((out[cap : len(data) + 8] != -1).sum()) == 0, "wrote past the capacity"
+    bad = b'["\xc0\x80", "' + b"x" * 70000 + b'"]'
+    for flags in (0, 1):
+        w = oracle.stage1(bad, flags=flags, impl="ref")
+        res, out = run_device(dev, scratch, bad, flags=flags, warps=16, kernel="split")
+        assert_same(res, out, w)
+        assert res.error == (11 if flags else 0)
+    res, out = run_device(dev, scratch, bad, flags=4, warps=16, kernel="split")
+    assert res.error == 0 and res.utf8_error == -1
+
+
 def test_every_misalignment(dev, scratch):
     data = b'{"k":"v\\"x","a":[1,2,3],"u":"\xe2\x82\xac"}' * 300
     want = oracle.stage1(data)
@@ -254,6 +321,12 @@ def test_alternating_kernel_kinds_and_tile_shapes(dev, scratch):
     wa = oracle.stage1(a)
     for warps in (2, 32, 2, 2, 32, 32, 2, 16, 4, 32, 8, 2, 24, 2):
         res, out = run_device(dev, scratch, a, warps=warps)
+        assert_same(res, out, wa)
+    seq = [("split", 8), ("persistent", 2), ("tile", 2), ("split", 16), ("split", 8), ("dataflow", 8), ("tile", 8), ("split", 8),
+           ("persistent", 16), ("dataflow", 4), ("dataflow", 4), ("split", 16), ("stream", 8), ("stream", 8), ("tile", 2),
+           ("stream", 2), ("persistent", 2), ("stream", 16), ("split", 8), ("stream", 4)]
+    for kernel, warps in seq:
+        res, out = run_device(dev, scratch, a, warps=warps, kernel=kernel)
         assert_same(res, out, wa)
 
 
