@@ -500,9 +500,16 @@ __device__ __forceinline__ void flatten_word(uint32_t *&dst, uint32_t bits, uint
         r &= ~(1u << h);
     }
 #else
-    while (bits) {
-        *dst++ = v31 - 31u + (uint32_t)(__ffs((int)bits) - 1);
-        bits &= bits - 1;
+    // The word is bit-reversed once; bfind (FLO in SASS) then returns 31 - (position of the lowest structural) directly.
+    // Per index: FLO, subtract, shift, xor (also sets the loop predicate), store, pointer bump, branch.  bfind is
+    // inline PTX on purpose: written with __clz / __ffs the compiler re-derives the position as 31 - FLO and clears
+    // the bit with a shifted 0x80000000 and a separate NOT, three instructions more per index.
+    uint32_t r = __brev(bits);
+    while (r) {
+        uint32_t h;
+        asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(r));
+        *dst++ = v31 - h;
+        r ^= 1u << h;   // bit h is set: xor clears it (and-not costs a separate NOT here)
     }
 #endif
 }

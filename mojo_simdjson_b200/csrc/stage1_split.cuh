@@ -212,43 +212,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(SplitCfg<NW>::MAXRE
     }
 }
 
-#ifndef SJ_K3_FLATTEN
-#define SJ_K3_FLATTEN 1   // 0: the fused kernels' flatten_to, 1: bit-reversed once + one FLO per index, 3: one POPC per index
-#endif
 #ifndef SJ_K3_MINCTAS
 #define SJ_K3_MINCTAS 8   // resident CTAs per SM the flatten kernel's register budget allows (8 -> 32 registers)
 #endif
-
-// The flatten kernel is bound by the XU pipe (BREV, FLO, POPC: 0.5 warp instructions / clock / SM): one XU operation per
-// index instead of the two of __ffs.
-__device__ __forceinline__ void flatten_word_k3(uint32_t *&dst, uint32_t bits, uint32_t v0) {
-#if SJ_K3_FLATTEN == 3
-    const uint32_t vm1 = v0 - 1u;
-    while (bits) {
-        const uint32_t t = bits - 1u;
-        *dst++ = vm1 + (uint32_t)__popc(bits ^ t);
-        bits &= t;
-    }
-#else
-    // FLO returns the index of the highest set bit: on the reversed word that is 31 - (position of the lowest structural).
-    // Per index: FLO, subtract, shift, and-not (sets the loop predicate), store, pointer bump, branch.
-    uint32_t r = __brev(bits);
-    const uint32_t v31 = v0 + 31u;
-    while (r) {
-        const uint32_t h = 31u - (uint32_t)__clz((int)r);
-        *dst++ = v31 - h;
-        r &= ~(1u << h);
-    }
-#endif
-}
-__device__ __forceinline__ void flatten_to_k3(uint32_t *dst, uint64_t structural, uint32_t v0) {
-#if SJ_K3_FLATTEN == 0
-    flatten_to(dst, structural, v0);
-#else
-    flatten_word_k3(dst, (uint32_t)structural, v0);
-    flatten_word_k3(dst, (uint32_t)(structural >> 32), v0 + 32u);
-#endif
-}
 
 template <int FW>
 struct FlattenCfg {
@@ -256,6 +222,70 @@ struct FlattenCfg {
     static constexpr int WCAP = 512;
     static constexpr int SMEM_BYTES = FW * (WCAP + 4) * 4;
 };
+
+// The flatten kernel is bound by instruction issue, so its two inner pieces are written out by hand.
+//
+// flatten_word_pair: the structurals of one 32-bit word into shared memory at byte address `sptr`, two per trip.  The
+// word is bit-reversed, so bfind (FLO) returns 31 - position; xor clears the bit and its result predicates the second
+// half and the loop (LOP3 with predicate output): FLO, SHF, LOP3, IADD, STS twice, one pointer bump, one branch.
+__device__ __forceinline__ void flatten_word_pair(uint32_t sptr, uint32_t bits, uint32_t v31) {
+    uint32_t r = __brev(bits);
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 h, m, x, ptr;\n"
+        "mov.u32 ptr, %1;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@!p bra FW_DONE;\n"
+        "FW_LOOP:\n"
+        "bfind.u32 h, %0;\n"
+        "shl.b32 m, 1, h;\n"
+        "xor.b32 %0, %0, m;\n"
+        "sub.u32 x, %2, h;\n"
+        "st.shared.u32 [ptr], x;\n"
+        "setp.ne.u32 q, %0, 0;\n"
+        "bfind.u32 h, %0;\n"
+        "@q shl.b32 m, 1, h;\n"
+        "@q xor.b32 %0, %0, m;\n"
+        "@q sub.u32 x, %2, h;\n"
+        "@q st.shared.u32 [ptr+4], x;\n"
+        "add.u32 ptr, ptr, 8;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p bra FW_LOOP;\n"
+        "FW_DONE:\n"
+        "}\n"
+        : "+r"(r)
+        : "r"(sptr), "r"(v31)
+        : "memory");
+}
+
+// stage[a .. a+total) -> out[first .. first+total) by one warp, total <= 512: at most four predicated 16-byte copies per
+// lane plus the ragged head / tail entries (a = phase of `first` in its 16-byte line, so stage and out are congruent)
+__device__ __forceinline__ void copy_out_warp(const uint32_t *stage, uint32_t a, uint32_t total, uint32_t *out, uint64_t first,
+                                              uint64_t cap, uint32_t lane) {
+    const uint32_t end = a + total;
+    uint32_t *g0 = out + ((int64_t)first - (int64_t)a);   // 16-byte aligned, may point below `out` by up to 3 entries
+    if (first + total <= cap) {
+        const uint32_t v_lo = (a + 3u) >> 2, v_hi = end >> 2;
+        const uint32_t nvec = v_hi > v_lo ? v_hi - v_lo : 0u;      // whole vectors; none when the run is shorter than a line
+        const uint4 *sv = reinterpret_cast<const uint4 *>(stage) + lane;
+        uint4 *gv = reinterpret_cast<uint4 *>(g0) + lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = lane + 32u * k;
+            if (v - v_lo < nvec) gv[32 * k] = sv[32 * k];          // v_lo <= v < v_hi in one unsigned compare
+        }
+        if (lane < 8u) {
+            const uint32_t j = lane < 4u ? lane : 4u * v_hi + (lane - 4u);
+            const bool head = lane < 4u && j >= a && j < end && j < 4u * v_lo;
+            const bool tail = lane >= 4u && j < end && j >= a && v_hi >= v_lo;
+            if (head || tail) g0[j] = stage[j];
+        }
+    } else {
+        for (uint32_t j = a + lane; j < end; j += 32u)
+            if (first + (j - a) < cap) g0[j] = stage[j];
+    }
+}
 
 // chunks [chunk_begin, chunk_end): one warp each
 template <int FW>
@@ -266,21 +296,24 @@ __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS) stage1_flatten_kernel(
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw) + warp * (Cfg::WCAP + 4);
     const uint32_t c = chunk_begin + blockIdx.x * FW + warp;
     if (c >= chunk_end) return;
-    const uint32_t gave_up = P.spec_flag ? __ldg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carry
-    const uint64_t carry = __ldg(reinterpret_cast<const unsigned long long *>(P.carry + c));
+    const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carry
+    const uint64_t carry = __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c));
     if (P.spec_flag && gave_up == P.gen) return;
     const uint32_t s_w = (uint32_t)(carry >> 63);
     const uint64_t first = carry & CARRY_RANK_MASK;
     const uint64_t structural = __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)c * 64 + s_w * 32 + lane));
-    const uint32_t cnt = (uint32_t)__popcll(structural);
+    const uint32_t lo = (uint32_t)structural, hi = (uint32_t)(structural >> 32);
+    const uint32_t cnt_lo = (uint32_t)__popc(lo), cnt = cnt_lo + (uint32_t)__popc(hi);
     const uint32_t incl = warp_inclusive_sum(cnt);
     const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
     const uint32_t v0 = c * 2048u + (uint32_t)lane * 64u - P.mis;
     if (wtotal <= (uint32_t)Cfg::WCAP) {
         const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
-        flatten_to_k3(stage + a + (incl - cnt), structural, v0);
+        const uint32_t sp = smem_u32(stage) + 4u * (a + (incl - cnt));
+        flatten_word_pair(sp, lo, v0 + 31u);
+        flatten_word_pair(sp + 4u * cnt_lo, hi, v0 + 63u);
         __syncwarp();
-        copy_out(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane, 32u);
+        copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
     } else {
         flatten_direct(P.out, P.cap, first + (incl - cnt), structural, v0);
     }

@@ -237,6 +237,35 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
         assert_same(res, out, wbad)
 
 
+@pytest.mark.parametrize("kernel", ["stream", "split", "persistent"])
+def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
+    """2 KiB chunks that contribute no index (inside a long string) at every 16-byte phase of the output cursor, and chunks
+    that contribute 1, 2, 3 indexes: the flatten kernel's vector copy must not touch a neighbour's entries."""
+    for k in range(0, 9):
+        for tail_items in (0, 1, 2, 3, 5):
+            data = b"[" + b"1," * k + b'"' + b"s" * 9000 + b'"' + b",2" * tail_items + b"]" + b" " * 2500 + b"\n[]"
+            want = oracle.stage1(data, impl="ref")
+            for mis in (0, 4, 8, 12):
+                res, out = run_device(dev, scratch, data, mis=mis, warps=8, kernel=kernel)
+                try:
+                    assert_same(res, out, want)
+                except AssertionError as e:  # pragma: no cover
+                    raise AssertionError(f"k={k} tail_items={tail_items} mis={mis} kernel={kernel}") from e
+    # output buffer at every 4-byte phase of a 16-byte line
+    data = b"[" + b"1," * 5 + b'"' + b"s" * 5000 + b'",' + b"[]," * 700 + b"0]"
+    want = oracle.stage1(data, impl="ref")
+    inp = scratch.put(data, 0)
+    for shift in range(4):
+        scratch.out[: len(data) + 16].fill_(-1)
+        dev.set_kernel(kernel)
+        dev.set_warps(8)
+        res = dev.index(inp, scratch.out[shift:])
+        dev.set_kernel("auto")
+        dev.set_warps(0)
+        assert_same(res, scratch.out[shift:], want)
+        assert int((scratch.out[:shift] != -1).sum()) == 0
+
+
 def test_split_pair_capacity_and_flags(dev, scratch):
     data = b'[' + b'1,' * 40000 + b'1]'
     want = oracle.stage1(data, impl="fast")
