@@ -303,6 +303,7 @@ struct LaneInput {
     uint32_t prev;    // the 4 bytes before them (UTF-8 look-behind)
     PrevState wst;    // carries entering the warp
     int64_t g0;       // aligned coordinate of the lane's first byte
+    uint32_t ends;    // the document ends exactly at this lane's last byte (only ever set in the last tile / chunk)
 };
 struct LanePhase1 {
     uint64_t m0, m1;  // structural bits if the warp starts outside / inside a string
@@ -333,7 +334,9 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
         in.w[4 * q + 3] = v.w;
     }
     in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_tile + off - 4) : 0u;
+    in.ends = 0;
     if (edge) {  // only the first and last tile: bytes outside [mis, alen) read as 0x20 (reference tail padding)
+        in.ends = in.g0 + 64 == alen;
 #pragma unroll
         for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
         if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
@@ -345,7 +348,6 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
 
 template <bool UTF8>
 __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P) {
-    const int64_t alen = (int64_t)P.alen;
     LaneMasks m;
     uint32_t u8err = 0;
     {
@@ -371,7 +373,7 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 const Utf8Carry uc = utf8_carry_from_prev_word(in.prev);
                 uint32_t tail_must;
                 const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
-                u8err = (ue != 0) || (in.g0 + 64 == alen && tail_must != 0);
+                u8err = (ue != 0) || (in.ends && tail_must != 0);
             }
         }
     }

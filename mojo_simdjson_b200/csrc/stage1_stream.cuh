@@ -41,14 +41,11 @@ struct StreamCfg {
 };
 
 // phase 1 input of one lane from the warp's private buffer; `chunk` points at the chunk's first byte, HALO bytes before it
-// are the preceding input (chunk > 0)
+// are the preceding input (chunk > 0).  `edge`: first chunk, or a last chunk that is not full.
 template <bool UTF8>
-__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, const Stage1Params &P,
+__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, bool edge, const Stage1Params &P,
                                            uint32_t &unresolved) {
-    const int64_t alen = (int64_t)P.alen;
-    const int64_t cb = (int64_t)c * 2048;
-    in.g0 = cb + lane * 64;
-    const bool edge = (c == 0) || (cb + 2048 > alen);
+    in.g0 = (int64_t)c * 2048 + lane * 64;
     const uint4 *src = reinterpret_cast<const uint4 *>(chunk + lane * 64);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -59,7 +56,10 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
         in.w[4 * q + 3] = v.w;
     }
     in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(chunk + lane * 64 - 4) : 0u;
-    if (edge) {  // first / last chunk: bytes outside [mis, alen) read as 0x20 (reference tail padding)
+    in.ends = 0;
+    if (edge) {  // bytes outside [mis, alen) read as 0x20 (reference tail padding)
+        const int64_t alen = (int64_t)P.alen;
+        in.ends = in.g0 + 64 == alen;
 #pragma unroll
         for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
         if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
@@ -82,51 +82,70 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *bufs = smem_raw + warp * (DEPTH * Cfg::BUF);
+    const uint32_t buf0 = smem_u32(smem_raw) + warp * (DEPTH * Cfg::BUF);   // shared-space addresses: 32-bit arithmetic only
+    const uint8_t *bufs = smem_raw + warp * (DEPTH * Cfg::BUF);
     const uint32_t bar0 = smem_u32(&s_bar[warp * DEPTH]);
     const uint32_t gw = blockIdx.x * NW + warp, stride = gridDim.x * NW;
+    // every chunk is 2048 bytes except possibly the last one; every chunk but chunk 0 has HALO bytes of look-behind
+    const uint32_t last = nchunks - 1u;
+    const uint32_t last_bytes = (uint32_t)(P.alen - (uint64_t)last * 2048u);   // 1 .. 2048
+    const uint32_t last_tx = ((last_bytes + 15u) & ~15u) + Cfg::HALO;          // stays inside the last 16-byte line of the data
+    const bool last_partial = last_bytes < 2048u;
 
-    auto fetch = [&](uint32_t c, int b) {  // lane 0: start the bulk copy of chunk c (+ look-behind) into buffer b
-        const int64_t cb = (int64_t)c * 2048;
-        int64_t nbytes = (int64_t)P.alen - cb;
-        nbytes = nbytes > 2048 ? 2048 : nbytes;
-        nbytes = (nbytes + 15) & ~15ll;                      // stays inside the last 16-byte line of the data
-        const uint32_t halo = c > 0 ? (uint32_t)Cfg::HALO : 0u;
-        mbar_expect_tx(bar0 + 8 * b, (uint32_t)nbytes + halo);
-        bulk_load(smem_u32(bufs) + b * Cfg::BUF + Cfg::HALO - halo, P.abase + cb - halo, (uint32_t)nbytes + halo, bar0 + 8 * b);
+    // lane 0: start the bulk copy of chunk c (> 0; source pointer already at its look-behind) into buffer b
+    auto fetch = [&](uint32_t c, const uint8_t *src, int b) {
+        const uint32_t tx = c == last ? last_tx : 2048u + Cfg::HALO;
+        mbar_expect_tx(bar0 + 8 * b, tx);
+        bulk_load(buf0 + b * Cfg::BUF, src, tx, bar0 + 8 * b);
     };
+    const uint8_t *src_next = P.abase + (size_t)gw * 2048u - Cfg::HALO;        // look-behind of this warp's next chunk to fetch
+    const size_t src_step = (size_t)stride * 2048u;
+    uint32_t c_next = gw;
     if (lane == 0) {
         for (int b = 0; b < DEPTH; b++) mbar_init(bar0 + 8 * b, 1);
         fence_mbar_init();
         for (int b = 0; b < DEPTH; b++) {
-            const uint64_t c = (uint64_t)gw + (uint64_t)b * stride;
-            if (c < nchunks) fetch((uint32_t)c, b);
+            if (c_next < nchunks) {
+                if (c_next == 0) {   // the document's first chunk: nothing before it
+                    const uint32_t tx = (nchunks == 1u ? last_tx : 2048u + Cfg::HALO) - Cfg::HALO;
+                    mbar_expect_tx(bar0 + 8 * b, tx);
+                    bulk_load(buf0 + b * Cfg::BUF + Cfg::HALO, P.abase, tx, bar0 + 8 * b);
+                } else {
+                    fetch(c_next, src_next, b);
+                }
+            }
+            c_next += stride;
+            src_next += src_step;
         }
     }
+    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);   // (only lane 0 uses src_next)
     __syncwarp();
-    uint32_t k = 0;
     int b = 0;
     uint32_t phase = 0;
-    for (uint64_t c64 = gw; c64 < nchunks; c64 += stride, k++) {
-        const uint32_t c = (uint32_t)c64;
+    uint64_t *mp = P.masks + (size_t)gw * 64 + lane;
+    uint4 *sp = reinterpret_cast<uint4 *>(P.chunk_sum) + gw;
+    for (uint32_t c = gw; c < nchunks; c += stride) {
         mbar_wait(bar0 + 8 * b, phase);
         LanePhase1 ph;
         {
             LaneInput in;
             uint32_t unresolved;
-            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, P, unresolved);
+            const bool edge = (c == 0u) || (c == last && last_partial);
+            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, P, unresolved);
             __syncwarp();  // every lane has its bytes in registers: the buffer can be refilled
             if (lane == 0) {
-                const uint64_t cn = c64 + (uint64_t)DEPTH * stride;
-                if (cn < nchunks) fetch((uint32_t)cn, b);
+                if (c_next < nchunks) fetch(c_next, src_next, b);
+                src_next += src_step;
                 if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
             }
+            c_next += stride;
             warp_compute<UTF8>(ph, in, lane, P);
         }
-        uint64_t *mp = P.masks + (size_t)c * 64 + lane;
         __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
         __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
-        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
+        if (lane == 0) *sp = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
+        mp += (size_t)stride * 64;
+        sp += stride;
         if (++b == DEPTH) {
             b = 0;
             phase ^= 1u;

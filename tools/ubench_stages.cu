@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_classify(const uint8_t *in, uint
 #pragma unroll
         for (int q = 0; q < 4; q++) { const uint4 v = s4[q]; li.w[4*q] = v.x; li.w[4*q+1] = v.y; li.w[4*q+2] = v.z; li.w[4*q+3] = v.w; }
         li.prev = *reinterpret_cast<const uint32_t *>(mine + lane * 64 - 4);
-        li.wst.e = 0; li.wst.p = 0; li.wst.unresolved = 0;
+        li.wst.e = 0; li.wst.p = 0; li.wst.unresolved = 0; li.ends = 0;
         li.g0 = 64 + (int64_t)chunk * 2048 + lane * 64;
         __syncwarp();
         LanePhase1 ph;
@@ -81,7 +81,7 @@ __global__ void k_make_masks(const uint8_t *in, uint64_t nchunks, uint4 *masks, 
     LaneInput li;
     const uint4 *s4 = reinterpret_cast<const uint4 *>(mine + lane * 64);
     for (int q = 0; q < 4; q++) { const uint4 v = s4[q]; li.w[4*q] = v.x; li.w[4*q+1] = v.y; li.w[4*q+2] = v.z; li.w[4*q+3] = v.w; }
-    li.prev = 0x20202020u; li.wst.e = 0; li.wst.p = 0; li.wst.unresolved = 0; li.g0 = 64 + (int64_t)chunk * 2048 + lane * 64;
+    li.prev = 0x20202020u; li.wst.e = 0; li.wst.p = 0; li.wst.unresolved = 0; li.ends = 0; li.g0 = 64 + (int64_t)chunk * 2048 + lane * 64;
     LanePhase1 ph;
     warp_compute<UTF8>(ph, li, lane, P);
     masks[chunk * 32 + lane] = make_uint4((uint32_t)ph.m0, (uint32_t)(ph.m0 >> 32), (uint32_t)ph.m1, (uint32_t)(ph.m1 >> 32));
