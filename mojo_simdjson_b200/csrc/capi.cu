@@ -20,9 +20,14 @@ namespace {
 
 constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
-// documents from this size on use the four-launch stream pipeline (its fixed cost, ~25 us of launch boundaries, is
-// recovered at ~150 MiB on a B200: 256 MiB 1372 vs 1278 GB/s, 64 MiB 935 vs 1096 GB/s)
-constexpr uint64_t SPLIT_MIN_BYTES = 192ull << 20;
+// Kernel organisation by document size (device-resident documents; measured on a B200 with the tile shape pick_warps
+// chooses, GB/s of input):
+//            16 MiB  32 MiB  64 MiB  128 MiB  256 MiB  1 GiB
+//   fused      636     906    1096     1216     1285   1345    one persistent kernel
+//   split       -      858    1117     1327     1432   1532    persistent classify + flatten (2 launches)
+//   stream     420     699    1006     1276     1499   1730    per-warp classify, 2 scan launches, flatten (+ no-op fallback)
+constexpr uint64_t SPLIT_MIN_BYTES = 64ull << 20;
+constexpr uint64_t STREAM_MIN_BYTES = 192ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
@@ -249,7 +254,7 @@ void free_split_scratch(sjb200_ctx *c) {
 }
 
 int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap,
-                      uint32_t flags, uint32_t slot, int32_t *d_status) {
+                      uint32_t flags, uint32_t slot, int32_t *d_status, bool whole_document = true) {
     Stage1Params &p = d.p;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
     p.mis = (uint32_t)(addr & 15u);
@@ -284,7 +289,11 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
         if (e && strcmp(e, "stream") == 0) env_kind = SJB200_KERNEL_STREAM;
     }
     int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : env_kind;
-    if (kind == SJB200_KERNEL_AUTO) kind = p.alen >= SPLIT_MIN_BYTES ? SJB200_KERNEL_STREAM : SJB200_KERNEL_PERSISTENT;
+    if (kind == SJB200_KERNEL_AUTO) {
+        kind = SJB200_KERNEL_PERSISTENT;
+        if (whole_document && p.alen >= SPLIT_MIN_BYTES) kind = SJB200_KERNEL_SPLIT;
+        if (whole_document && p.alen >= STREAM_MIN_BYTES) kind = SJB200_KERNEL_STREAM;
+    }
     d.stream = kind == SJB200_KERNEL_STREAM;
     if (d.stream && d.warps > 24) d.warps = 16;   // shape of the fallback (persistent) launch
     d.split = kind == SJB200_KERNEL_SPLIT && (d.warps == 8 || d.warps == 16);
@@ -602,7 +611,7 @@ int32_t sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, uint64_t len, uint32_t 
     c->slot = (c->slot + 1) % RESULT_SLOTS;
     c->last_flags = flags;
     DocPlan d;
-    rc = plan_document(c, d, c->d_in, len, c->d_out, cap, flags, c->slot, nullptr);
+    rc = plan_document(c, d, c->d_in, len, c->d_out, cap, flags, c->slot, nullptr, /*whole_document=*/false);  // indexed chunk by chunk
     if (rc != SJB200_SUCCESS) return rc;
     // Streaming: the document goes to the device in chunks of whole tiles; chunk k is indexed by its own launch as soon
     // as it has arrived (same generation: the look-back carries parity and cursor across launches), and its indexes

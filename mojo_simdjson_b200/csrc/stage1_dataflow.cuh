@@ -224,7 +224,7 @@ __global__ void __launch_bounds__((2 * NC + 1) * 32) __maxnreg__(FlowCfg<NC>::MA
                 const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
                 flatten_to(stage + a + (incl - cnt), structural, v0);
                 __syncwarp();
-                copy_out(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane, 32u);
+                copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
                 __syncwarp();  // the staging area is reused by the next tile
             } else {
                 flatten_direct(P.out, P.cap, first + (incl - cnt), structural, v0);

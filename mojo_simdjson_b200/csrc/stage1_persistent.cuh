@@ -178,7 +178,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
                 const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
                 flatten_to(stage + a + (incl - cnt), structural, old.v0);
                 __syncwarp();
-                copy_out(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane, 32u);
+                copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
                 __syncwarp();  // the staging area is reused by the next tile
 #if SJ_TRACE
                 if (lane == 0 && (warp == 0 || warp == NW - 1)) TRACE(P, S.tile, warp == 0 ? 12 : 13, gtime());  // flush done

@@ -223,70 +223,6 @@ struct FlattenCfg {
     static constexpr int SMEM_BYTES = FW * (WCAP + 4) * 4;
 };
 
-// The flatten kernel is bound by instruction issue, so its two inner pieces are written out by hand.
-//
-// flatten_word_pair: the structurals of one 32-bit word into shared memory at byte address `sptr`, two per trip.  The
-// word is bit-reversed, so bfind (FLO) returns 31 - position; xor clears the bit and its result predicates the second
-// half and the loop (LOP3 with predicate output): FLO, SHF, LOP3, IADD, STS twice, one pointer bump, one branch.
-__device__ __forceinline__ void flatten_word_pair(uint32_t sptr, uint32_t bits, uint32_t v31) {
-    uint32_t r = __brev(bits);
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .u32 h, m, x, ptr;\n"
-        "mov.u32 ptr, %1;\n"
-        "setp.ne.u32 p, %0, 0;\n"
-        "@!p bra FW_DONE;\n"
-        "FW_LOOP:\n"
-        "bfind.u32 h, %0;\n"
-        "shl.b32 m, 1, h;\n"
-        "xor.b32 %0, %0, m;\n"
-        "sub.u32 x, %2, h;\n"
-        "st.shared.u32 [ptr], x;\n"
-        "setp.ne.u32 q, %0, 0;\n"
-        "bfind.u32 h, %0;\n"
-        "@q shl.b32 m, 1, h;\n"
-        "@q xor.b32 %0, %0, m;\n"
-        "@q sub.u32 x, %2, h;\n"
-        "@q st.shared.u32 [ptr+4], x;\n"
-        "add.u32 ptr, ptr, 8;\n"
-        "setp.ne.u32 p, %0, 0;\n"
-        "@p bra FW_LOOP;\n"
-        "FW_DONE:\n"
-        "}\n"
-        : "+r"(r)
-        : "r"(sptr), "r"(v31)
-        : "memory");
-}
-
-// stage[a .. a+total) -> out[first .. first+total) by one warp, total <= 512: at most four predicated 16-byte copies per
-// lane plus the ragged head / tail entries (a = phase of `first` in its 16-byte line, so stage and out are congruent)
-__device__ __forceinline__ void copy_out_warp(const uint32_t *stage, uint32_t a, uint32_t total, uint32_t *out, uint64_t first,
-                                              uint64_t cap, uint32_t lane) {
-    const uint32_t end = a + total;
-    uint32_t *g0 = out + ((int64_t)first - (int64_t)a);   // 16-byte aligned, may point below `out` by up to 3 entries
-    if (first + total <= cap) {
-        const uint32_t v_lo = (a + 3u) >> 2, v_hi = end >> 2;
-        const uint32_t nvec = v_hi > v_lo ? v_hi - v_lo : 0u;      // whole vectors; none when the run is shorter than a line
-        const uint4 *sv = reinterpret_cast<const uint4 *>(stage) + lane;
-        uint4 *gv = reinterpret_cast<uint4 *>(g0) + lane;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t v = lane + 32u * k;
-            if (v - v_lo < nvec) gv[32 * k] = sv[32 * k];          // v_lo <= v < v_hi in one unsigned compare
-        }
-        if (lane < 8u) {
-            const uint32_t j = lane < 4u ? lane : 4u * v_hi + (lane - 4u);
-            const bool head = lane < 4u && j >= a && j < end && j < 4u * v_lo;
-            const bool tail = lane >= 4u && j < end && j >= a && v_hi >= v_lo;
-            if (head || tail) g0[j] = stage[j];
-        }
-    } else {
-        for (uint32_t j = a + lane; j < end; j += 32u)
-            if (first + (j - a) < cap) g0[j] = stage[j];
-    }
-}
-
 // chunks [chunk_begin, chunk_end): one warp each
 template <int FW>
 __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
@@ -311,7 +247,7 @@ __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS) stage1_flatten_kernel(
         const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
         const uint32_t sp = smem_u32(stage) + 4u * (a + (incl - cnt));
         flatten_word_pair(sp, lo, v0 + 31u);
-        flatten_word_pair(sp + 4u * cnt_lo, hi, v0 + 63u);
+        flatten_word_pair(sp + 4u * cnt_lo, hi, v0 + 63u);   // (the popcount of the low word is needed for the scan anyway)
         __syncwarp();
         copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
     } else {
