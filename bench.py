@@ -370,7 +370,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # which kernel organisation the library picks for this document size (capi.cu: SPLIT_MIN_BYTES) unless forced
     seg = size / nseg
-    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (192 << 20) else ("split" if seg >= (64 << 20) else "persistent"))
+    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (128 << 20) else ("split" if seg >= (48 << 20) else "persistent"))
     prof = ncu_traffic(kind)
     if kind == "stream":
         kname = ("stage-1 stream pipeline, 5 launches per document: stage1_stream_classify_kernel -> stage1_span_reduce_kernel -> "

@@ -21,13 +21,13 @@ namespace {
 constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
 // Kernel organisation by document size (device-resident documents; measured on a B200 with the tile shape pick_warps
-// chooses, GB/s of input):
-//            16 MiB  32 MiB  64 MiB  128 MiB  256 MiB  1 GiB
-//   fused      636     906    1096     1216     1285   1345    one persistent kernel
-//   split       -      858    1117     1327     1432   1532    persistent classify + flatten (2 launches)
-//   stream     420     699    1006     1276     1499   1730    per-warp classify, 2 scan launches, flatten (+ no-op fallback)
-constexpr uint64_t SPLIT_MIN_BYTES = 64ull << 20;
-constexpr uint64_t STREAM_MIN_BYTES = 192ull << 20;
+// chooses and programmatic dependent launch between the launches of a document, GB/s of input; tools/sizesweep.py):
+//            16 MiB  32 MiB  48 MiB  64 MiB  96 MiB  128 MiB  192 MiB  256 MiB  1 GiB
+//   fused      635     907     996    1091    1172     1212     1261     1284   1348   one persistent kernel
+//   split      658     905    1044    1193    1270     1348     1413     1446   1535   persistent classify + flatten
+//   stream     528     799     995    1092    1259     1360     1488     1558   1752   per-warp classify, 2 scans, flatten
+constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
+constexpr uint64_t STREAM_MIN_BYTES = 128ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
@@ -67,6 +67,7 @@ struct sjb200_ctx {
     uint64_t *d_masks = nullptr;           // split pair: the two structural mask planes of every 2 KiB chunk
     uint64_t *d_carry = nullptr;           //             one carry word per chunk
     uint64_t split_chunks = 0;             //             chunks the two arrays hold (allocated on first use)
+    bool scratch_failed = false;           //             that allocation failed once: automatic choice stays with the fused kernel
     uint32_t *d_chunk_sum = nullptr;       // stream pipeline: per-chunk and per-1024-chunk summaries, speculation flag
     uint32_t *d_block_sum = nullptr;
     uint32_t *d_spec_flag = nullptr;
@@ -151,6 +152,31 @@ cudaError_t prepare_flow(int *occ) {
     if (*occ < 1) *occ = 1;
     return e;
 }
+// Launch `kernel` so that it may be scheduled while the previous kernel of the stream drains (programmatic dependent
+// launch); the kernel itself waits for its predecessor (griddepcontrol.wait) before it reads anything.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+bool use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SJB200_PDL");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 template <int NW, bool UTF8>
 cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = SplitCfg<NW>;
@@ -161,8 +187,7 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     if (e != cudaSuccess) return e;
     constexpr int FW = 8;
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
-    stage1_flatten_kernel<FW><<<(c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s>>>(p, c0, c1);
-    return cudaGetLastError();
+    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, use_pdl(), p, c0, c1);
 }
 #ifndef SJ_STREAM_NW
 #define SJ_STREAM_NW 8
@@ -175,12 +200,15 @@ cudaError_t launch_stream(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
     stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
+    cudaError_t e = cudaGetLastError();
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
-    stage1_span_reduce_kernel<<<nblocks, 1024, 0, s>>>(p, nchunks);
-    stage1_span_carries_kernel<<<nblocks, 1024, 0, s>>>(p, nchunks);
+    const bool pdl = use_pdl();
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     constexpr int FW = 8;
-    stage1_flatten_kernel<FW><<<(nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s>>>(p, 0u, nchunks);
-    return cudaGetLastError();
+    if (e == cudaSuccess)
+        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
+    return e;
 }
 cudaError_t prepare_stream(int *occ) {
     using Cfg = StreamCfg<STREAM_NW>;
@@ -289,10 +317,11 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
         if (e && strcmp(e, "stream") == 0) env_kind = SJB200_KERNEL_STREAM;
     }
     int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : env_kind;
-    if (kind == SJB200_KERNEL_AUTO) {
+    const bool auto_kind = kind == SJB200_KERNEL_AUTO;
+    if (auto_kind) {
         kind = SJB200_KERNEL_PERSISTENT;
-        if (whole_document && p.alen >= SPLIT_MIN_BYTES) kind = SJB200_KERNEL_SPLIT;
-        if (whole_document && p.alen >= STREAM_MIN_BYTES) kind = SJB200_KERNEL_STREAM;
+        if (whole_document && !c->scratch_failed && p.alen >= SPLIT_MIN_BYTES) kind = SJB200_KERNEL_SPLIT;
+        if (whole_document && !c->scratch_failed && p.alen >= STREAM_MIN_BYTES) kind = SJB200_KERNEL_STREAM;
     }
     d.stream = kind == SJB200_KERNEL_STREAM;
     if (d.stream && d.warps > 24) d.warps = 16;   // shape of the fallback (persistent) launch
@@ -325,7 +354,17 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
                 cudaMalloc(&c->d_spec_flag, 256) != cudaSuccess || cudaMemset(c->d_spec_flag, 0, 256) != cudaSuccess) {
                 free_split_scratch(c);
                 cudaGetLastError();
-                return SJB200_MEMALLOC;
+                if (!auto_kind) return SJB200_MEMALLOC;   // the caller asked for this organisation explicitly
+                // chosen automatically: the fused kernel needs no scratch; do not try again for this context
+                c->scratch_failed = true;
+                d.split = d.stream = false;
+                d.warps = pick_warps(c, p.alen);
+                d.persist = d.warps <= 24;
+                const uint64_t t2 = (uint64_t)d.warps * 2048;
+                p.ntiles = (uint32_t)((p.alen + t2 - 1) / t2);
+                p.tile_end = p.ntiles;
+                p.ticket = d.persist ? c->ticket : c->ticket + 2;
+                return SJB200_SUCCESS;
             }
             c->split_chunks = n;
         }

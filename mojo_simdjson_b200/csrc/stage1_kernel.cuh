@@ -127,6 +127,9 @@ __device__ __forceinline__ uint64_t gtime() {
 #else
 #define TRACE(P, tile, slot, val) do { } while (0)
 #endif
+// Programmatic dependent launch: blocks until the kernel this one depends on has completed and its writes are visible.
+// A no-op when the kernel was launched without the attribute.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

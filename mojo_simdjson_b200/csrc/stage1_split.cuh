@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS) stage1_flatten_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw) + warp * (Cfg::WCAP + 4);
     const uint32_t c = chunk_begin + blockIdx.x * FW + warp;
+    grid_dependency_wait();
     if (c >= chunk_end) return;
     const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carry
     const uint64_t carry = __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c));

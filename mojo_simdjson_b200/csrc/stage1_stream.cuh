@@ -209,6 +209,7 @@ constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries pe
 
 __global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks) {
     __shared__ uint4 s_w[32];
+    grid_dependency_wait();
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
     const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     SpanAcc mine = span_empty();
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Pa
 
 __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1Params P, uint32_t nchunks) {
     __shared__ uint4 s_w[32];
+    grid_dependency_wait();
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
     const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     uint4 sum[SPAN_PER_THREAD];
