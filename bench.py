@@ -57,7 +57,7 @@ def ncu_traffic(kind: str):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, ~2 ms period)."""
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, ~4 ms period)."""
 
     def __init__(self, device_index: int):
         super().__init__(daemon=True)
@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def stop(self):
         self._stop_evt.set()
@@ -299,8 +299,9 @@ def run_ours(args):
             if rc != errors.SUCCESS:
                 raise RuntimeError(f"launch failed: {errors.NAMES.get(rc, rc)}")
         else:
-            # every segment's kernel, then the verdict exchange (all-reduce MAX of the error flag, all-gather of the
-            # per-segment counts), enqueued behind the kernels with no host round trip
+            # every segment's kernels, then the verdict exchange (all-gather of the per-segment rows, all-reduce MAX of
+            # the error flags), issued asynchronously behind the kernels: no host round trip, and on the GPU it runs
+            # beside the kernels of the next pass
             last_exchange["worst"], last_exchange["counts"] = driver.enqueue(d_in, d_out, flags)
 
     # ---- correctness gate before any timing -------------------------------------------------------------
@@ -313,8 +314,9 @@ def run_ours(args):
         assert tr == [size & 0xFFFFFFFF, size & 0xFFFFFFFF, 0], tr
     else:
         step()
+        driver.flush()
         torch.cuda.synchronize()
-        if int(last_exchange["worst"].item()) != 0:
+        if int(last_exchange["worst"].max().item()) != 0:
             raise RuntimeError(f"stage 1 failed on an NDJSON segment: {driver._status.cpu().tolist()}")
         allc = last_exchange["counts"].cpu()
         n_total = int(allc[rank][allc[rank] >= 0].sum())
@@ -325,16 +327,20 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)   # NVML initialisation takes tens of ms with 8 processes: before the barrier, not after
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     ev0.record(stream)
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    if driver is not None:
+        driver.flush()   # the last verdict exchanges belong to the timed region
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to issue one pass (diagnostic)
     ev1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -370,7 +376,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # which kernel organisation the library picks for this document size (capi.cu: SPLIT_MIN_BYTES) unless forced
     seg = size / nseg
-    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (128 << 20) else ("split" if seg >= (48 << 20) else "persistent"))
+    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (160 << 20) else ("split" if seg >= (48 << 20) else "persistent"))
     prof = ncu_traffic(kind)
     if kind == "stream":
         kname = ("stage-1 stream pipeline, 5 launches per document: stage1_stream_classify_kernel -> stage1_span_reduce_kernel -> "
@@ -451,13 +457,22 @@ def run_ours(args):
                          f"CPU: {cpu_model()}, {os.cpu_count()} cores",
                "parity_checked_indexes": int(k)}
 
+    # per-rank picture (N > 1): every rank's own pass time without the exchange, own timed-region time and own clocks --
+    # the job-level number is the maximum over ranks, so one slower GPU shows up here
+    per_rank = None
+    if world > 1:
+        mine = {"kernel_ms": round(k_ms * nseg, 4), "timed_ms_per_step": round(ms_total / args.steps, 4),
+                "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(n_gpus, size),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "utf8_validation": not args.no_utf8, "segments_per_gpu": nseg,
+            "utf8_validation": not args.no_utf8, "segments_per_gpu": nseg, "host_enqueue_ms_per_step": round(host_enqueue_ms, 4), "per_rank": per_rank,
             "frac_of_aggregate_hbm": round(value * (alg_bytes * nseg / size) / (peak * n_gpus), 4),
         }
         print(json.dumps(line), flush=True)

@@ -82,7 +82,7 @@ int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
 /*
  * Force the kernel organisation (tuning / test knob; every choice produces identical results):
  *   AUTO        chosen from the document size: PERSISTENT below 48 MiB and for the chunked host path, SPLIT from 48 MiB,
- *               STREAM from 128 MiB on
+ *               STREAM from 160 MiB on
  *   TILE        one tile per CTA, look-back by warp 0
  *   PERSISTENT  persistent CTAs, compute warps + scan warp, classify and flatten fused
  *   DATAFLOW    persistent CTAs, classifier warps -> mask ring in shared memory -> flattener warps

@@ -10,6 +10,7 @@ runs on the GPU through libsimdjson_b200.so -- there is no CPU implementation in
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -74,48 +75,80 @@ class NdjsonBatchDriver:
         self.seg_bytes = min(seg_bytes, 0x7FFFFFFF)
         self.max_segments = max_segments
         self.group = group
-        self._status = None
+        self._status = None               # rows written by the most recent pass
         self._offsets = None
-        self._worst = None
+        self._bufs = None
+        self._last = None
+        self._pass = 0
+        # True: the exchange of a pass runs beside the kernels of the next one; False: strictly after its own pass
+        self.overlap_exchange = os.environ.get("SJB200_EXCHANGE", "async") != "sync"
 
     def plan(self, d_shard: torch.Tensor) -> list[int]:
         """Cuts the shard at newlines into segments of < 2 * seg_bytes (device-side search)."""
         self._offsets = self.ctx.split(d_shard, self.seg_bytes, self.max_segments)
         nseg = len(self._offsets) - 1
-        self._status = torch.zeros((max(nseg, 1), 2), dtype=torch.int32, device=d_shard.device)
+        if nseg > self.max_segments:
+            raise ValueError(f"{nseg} segments > max_segments={self.max_segments}")
+        self._status = torch.full((self.max_segments, 2), -1, dtype=torch.int32, device=d_shard.device)
         return self._offsets
 
     def index_capacity(self) -> int:
         return self._offsets[-1] + 3 * (len(self._offsets) - 1)
 
     def enqueue(self, d_shard: torch.Tensor, d_out: torch.Tensor, flags: int = 0):
-        """One pass: every segment's kernel, then the verdict exchange, all enqueued on the current stream.
+        """One pass: every segment's kernels on the current stream, then the verdict exchange -- an all-gather of the
+        per-segment {error, count} rows and an all-reduce(MAX) of the same rows -- issued asynchronously, so that on the
+        GPU it runs beside the kernels of the NEXT pass (two sets of buffers alternate; a set is reused only after the
+        exchange that read it has finished, a stream-level wait that never blocks the host).
 
-        Returns (worst, all_counts) like exchange_verdicts, using preallocated buffers: per pass this costs one tiny
-        reduction kernel, one all-reduce(MAX) on 4 bytes and one all-gather of max_segments int32 per rank."""
-        rc = self.ctx.run_segments_async(d_shard, self._offsets, d_out, self._status, flags)
+        Returns (errors, all_counts): errors int32 [max_segments] = per segment index the worst error over all ranks
+        (-1 = no rank has such a segment), all_counts int32 [world, max_segments] (-1 = no such segment).  Both are valid
+        once flush() has been enqueued and the stream synchronised (run() does that)."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if self._bufs is None:
+            dev = d_shard.device
+            self._bufs = [dict(status=torch.full((self.max_segments, 2), -1, dtype=torch.int32, device=dev),
+                               gathered=torch.empty(world * self.max_segments * 2, dtype=torch.int32, device=dev), works=())
+                          for _ in range(2)]
+        b = self._bufs[self._pass & 1]
+        self._pass += 1
+        for w in b["works"]:
+            w.wait()                       # the exchange of two passes ago must be done with these buffers
+        b["works"] = ()
+        rc = self.ctx.run_segments_async(d_shard, self._offsets, d_out, b["status"], flags)
         if rc != 0:
             raise RuntimeError(f"segment launch failed with error {rc}")
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        nseg = len(self._offsets) - 1
-        if self._worst is None:
-            dev = d_shard.device
-            self._worst = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._padded = torch.full((self.max_segments, 2), -1, dtype=torch.int32, device=dev)
-            self._gathered = torch.empty(world * self.max_segments * 2, dtype=torch.int32, device=dev)
-        torch.amax(self._status[:nseg, 0], dim=0, keepdim=True, out=self._worst)
-        self._padded[:nseg].copy_(self._status[:nseg])
+        self._status = b["status"]
         if world > 1:
-            dist.all_reduce(self._worst, op=dist.ReduceOp.MAX, group=self.group)
-            dist.all_gather_into_tensor(self._gathered, self._padded.reshape(-1), group=self.group)
-            allc = self._gathered.reshape(world, self.max_segments, 2)[:, :, 1]
+            # both collectives run in issue order on the communicator's stream: the gather reads the local rows before the
+            # in-place reduction turns them into the maximum over the ranks
+            overlap = self.overlap_exchange
+            w1 = dist.all_gather_into_tensor(b["gathered"], b["status"].reshape(-1), group=self.group, async_op=overlap)
+            w2 = dist.all_reduce(b["status"], op=dist.ReduceOp.MAX, group=self.group, async_op=overlap)
+            b["works"] = (w1, w2) if overlap else ()
+            allc = b["gathered"].reshape(world, self.max_segments, 2)[:, :, 1]
         else:
-            allc = self._padded[:, 1].reshape(1, self.max_segments)
-        return self._worst, allc
+            allc = b["status"][:, 1].reshape(1, self.max_segments)
+        self._last = b
+        return b["status"][:, 0], allc
+
+    def flush(self) -> None:
+        """Makes the current stream wait for every verdict exchange still in flight."""
+        for b in self._bufs or ():
+            for w in b["works"]:
+                w.wait()
+            b["works"] = ()
 
     def run(self, d_shard: torch.Tensor, d_out: torch.Tensor, flags: int = 0) -> BatchVerdict:
-        worst, all_counts = self.enqueue(d_shard, d_out, flags)
+        errors, all_counts = self.enqueue(d_shard, d_out, flags)
+        self.flush()
         torch.cuda.synchronize(d_shard.device)
-        st = self._status.cpu()
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        nseg = len(self._offsets) - 1
         counts = [[int(c) for c in row if c >= 0] for row in all_counts.cpu().tolist()]
-        return BatchVerdict(int(worst.item()), counts, [int(x) for x in st[:, 0]], [])
+        if world > 1:
+            mine = self._last["gathered"].reshape(world, self.max_segments, 2)[rank, :nseg, 0].cpu()
+        else:
+            mine = self._last["status"][:nseg, 0].cpu()
+        return BatchVerdict(int(errors.max().item()), counts, [int(x) for x in mine], [])

@@ -22,12 +22,12 @@ constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
 // Kernel organisation by document size (device-resident documents; measured on a B200 with the tile shape pick_warps
 // chooses and programmatic dependent launch between the launches of a document, GB/s of input; tools/sizesweep.py):
-//            16 MiB  32 MiB  48 MiB  64 MiB  96 MiB  128 MiB  192 MiB  256 MiB  1 GiB
-//   fused      635     907     996    1091    1172     1212     1261     1284   1348   one persistent kernel
-//   split      658     905    1044    1193    1270     1348     1413     1446   1535   persistent classify + flatten
-//   stream     528     799     995    1092    1259     1360     1488     1558   1752   per-warp classify, 2 scans, flatten
+//            16 MiB  32 MiB  48 MiB  64 MiB  96 MiB  128 MiB  256 MiB  1 GiB
+//   fused      635     907     996    1091    1172     1212     1284   1348   one persistent kernel
+//   split      658     905    1044    1173    1269     1354     1445   1536   persistent classify + flatten
+//   stream     528     799     995    1023    1153     1295     1542   1794   per-warp classify, 2 scans, flatten
 constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
-constexpr uint64_t STREAM_MIN_BYTES = 128ull << 20;
+constexpr uint64_t STREAM_MIN_BYTES = 160ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;

@@ -1,8 +1,8 @@
 // stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of four stream-ordered launches with no
 // waiting between warps, CTAs or launches other than stream order:
 //
-//   stream_classify : every warp is its own pipeline.  Warp g handles the 2 KiB chunks g, g + G, g + 2G, ... (G = warps in
-//                     the grid), each fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
+//   stream_classify : every warp is its own pipeline.  A warp draws runs of 4 consecutive 2 KiB chunks from an atomic
+//                     counter, each chunk fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
 //                     mbarrier each) together with the 32 bytes before it, which decide the escape / scalar carries
 //                     entering the chunk.  Output per chunk: the two structural mask planes (string state entering the
 //                     chunk unknown -> one plane per parity) and a 16-byte summary {count0, count1, flags}.
@@ -75,77 +75,91 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
     in.wst = st;
 }
 
+// Chunks are handed out dynamically, TICKET_CHUNKS consecutive chunks per draw from P.ticket[3] (zero at launch; the scan
+// kernel that follows resets it).  A static partition would be slightly cheaper but assumes that every CTA of the grid is
+// resident from the start: with another kernel on the device (the NCCL verdict exchange of the previous pass, a second
+// context) a displaced CTA would start only when some other CTA has finished its whole share, doubling the kernel time.
+constexpr uint32_t TICKET_CHUNKS = 4;
+constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
+
 template <int NW, bool UTF8>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks) {
     using Cfg = StreamCfg<NW>;
     constexpr int DEPTH = Cfg::DEPTH;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
+    __shared__ uint32_t s_chunk[NW * DEPTH];                  // chunk held by each buffer, NO_CHUNK = nothing more to do
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t buf0 = smem_u32(smem_raw) + warp * (DEPTH * Cfg::BUF);   // shared-space addresses: 32-bit arithmetic only
     const uint8_t *bufs = smem_raw + warp * (DEPTH * Cfg::BUF);
     const uint32_t bar0 = smem_u32(&s_bar[warp * DEPTH]);
-    const uint32_t gw = blockIdx.x * NW + warp, stride = gridDim.x * NW;
+    volatile uint32_t *my_chunk = s_chunk + warp * DEPTH;
+    uint32_t *ticket = P.ticket + 3;
     // every chunk is 2048 bytes except possibly the last one; every chunk but chunk 0 has HALO bytes of look-behind
     const uint32_t last = nchunks - 1u;
     const uint32_t last_bytes = (uint32_t)(P.alen - (uint64_t)last * 2048u);   // 1 .. 2048
-    const uint32_t last_tx = ((last_bytes + 15u) & ~15u) + Cfg::HALO;          // stays inside the last 16-byte line of the data
+    const uint32_t last_tx = (last_bytes + 15u) & ~15u;                        // stays inside the last 16-byte line of the data
     const bool last_partial = last_bytes < 2048u;
 
-    // lane 0: start the bulk copy of chunk c (> 0; source pointer already at its look-behind) into buffer b
-    auto fetch = [&](uint32_t c, const uint8_t *src, int b) {
-        const uint32_t tx = c == last ? last_tx : 2048u + Cfg::HALO;
-        mbar_expect_tx(bar0 + 8 * b, tx);
-        bulk_load(buf0 + b * Cfg::BUF, src, tx, bar0 + 8 * b);
+    // lane 0 only: the next chunk of this warp.  The draw for the ticket after the current one is already in flight, so the
+    // atomic's latency is never waited for.
+    // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3), so that a launch does not begin with thousands of
+    // atomics on one address; the counter hands out the chunks after those.
+    const uint32_t t_base = gridDim.x * NW * TICKET_CHUNKS;
+    uint32_t t_cur = 0, t_left = 0, t_next = (blockIdx.x * NW + warp) * TICKET_CHUNKS;
+    auto next_chunk = [&]() -> uint32_t {
+        if (t_left == 0) {
+            t_cur = t_next;
+            t_left = TICKET_CHUNKS;
+            t_next = t_base + atomicAdd(ticket, TICKET_CHUNKS);
+        }
+        const uint32_t c = t_cur + (TICKET_CHUNKS - t_left);
+        t_left--;
+        return c;
     };
-    const uint8_t *src_next = P.abase + (size_t)gw * 2048u - Cfg::HALO;        // look-behind of this warp's next chunk to fetch
-    const size_t src_step = (size_t)stride * 2048u;
-    uint32_t c_next = gw;
+    // lane 0 only: refill buffer b with the warp's next chunk (bulk copy of the chunk and its look-behind), or mark the end
+    auto fetch = [&](int b) {
+        const uint32_t c = next_chunk();
+        if (c < nchunks) {
+            my_chunk[b] = c;
+            const uint32_t halo = c > 0u ? (uint32_t)Cfg::HALO : 0u;
+            const uint32_t tx = (c == last ? last_tx : 2048u) + halo;
+            mbar_expect_tx(bar0 + 8 * b, tx);
+            bulk_load(buf0 + b * Cfg::BUF + Cfg::HALO - halo, P.abase + (size_t)c * 2048u - halo, tx, bar0 + 8 * b);
+        } else {
+            my_chunk[b] = NO_CHUNK;
+            mbar_arrive(bar0 + 8 * b);
+        }
+    };
     if (lane == 0) {
         for (int b = 0; b < DEPTH; b++) mbar_init(bar0 + 8 * b, 1);
         fence_mbar_init();
-        for (int b = 0; b < DEPTH; b++) {
-            if (c_next < nchunks) {
-                if (c_next == 0) {   // the document's first chunk: nothing before it
-                    const uint32_t tx = (nchunks == 1u ? last_tx : 2048u + Cfg::HALO) - Cfg::HALO;
-                    mbar_expect_tx(bar0 + 8 * b, tx);
-                    bulk_load(buf0 + b * Cfg::BUF + Cfg::HALO, P.abase, tx, bar0 + 8 * b);
-                } else {
-                    fetch(c_next, src_next, b);
-                }
-            }
-            c_next += stride;
-            src_next += src_step;
-        }
+        for (int b = 0; b < DEPTH; b++) fetch(b);
     }
-    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);   // (only lane 0 uses src_next)
     __syncwarp();
     int b = 0;
     uint32_t phase = 0;
-    uint64_t *mp = P.masks + (size_t)gw * 64 + lane;
-    uint4 *sp = reinterpret_cast<uint4 *>(P.chunk_sum) + gw;
-    for (uint32_t c = gw; c < nchunks; c += stride) {
+    while (true) {
         mbar_wait(bar0 + 8 * b, phase);
+        const uint32_t c = my_chunk[b];
+        if (c == NO_CHUNK) break;
         LanePhase1 ph;
         {
             LaneInput in;
             uint32_t unresolved;
             const bool edge = (c == 0u) || (c == last && last_partial);
             chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, P, unresolved);
-            __syncwarp();  // every lane has its bytes in registers: the buffer can be refilled
+            __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
             if (lane == 0) {
-                if (c_next < nchunks) fetch(c_next, src_next, b);
-                src_next += src_step;
+                fetch(b);
                 if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
             }
-            c_next += stride;
             warp_compute<UTF8>(ph, in, lane, P);
         }
+        uint64_t *mp = P.masks + (size_t)c * 64 + lane;
         __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
         __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
-        if (lane == 0) *sp = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
-        mp += (size_t)stride * 64;
-        sp += stride;
+        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
         if (++b == DEPTH) {
             b = 0;
             phase ^= 1u;
@@ -210,6 +224,7 @@ constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries pe
 __global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ticket[3] = 0;   // the classify kernel is done: its chunk counter is free again
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
     const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     SpanAcc mine = span_empty();

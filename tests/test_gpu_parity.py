@@ -474,3 +474,31 @@ def test_ndjson_batch_segments(dev):
         assert u8[s] == 0
         got = host[idx_offs[s] : idx_offs[s] + want.n + 3]
         assert np.array_equal(got, want.indexes)
+
+
+def test_ndjson_batch_driver_single_rank(dev):
+    """NdjsonBatchDriver without a process group: plan + two passes (alternating buffer sets) + run()."""
+    from mojo_simdjson_b200 import batch as batch_mod, synth
+
+    size = 24 << 20
+    data = synth.ndjson(size)
+    inp = torch.from_numpy(data).cuda()
+    drv = batch_mod.NdjsonBatchDriver(dev, seg_bytes=4 << 20, max_segments=16)
+    offs = drv.plan(inp)
+    assert offs[0] == 0 and offs[-1] == size and len(offs) - 1 >= 3
+    out = torch.empty(drv.index_capacity(), dtype=torch.int32, device="cuda")
+    want = [oracle.stage1(data[a:b], impl="fast") for a, b in zip(offs, offs[1:])]
+    for _ in range(3):
+        out.fill_(-1)
+        v = drv.run(inp, out)
+        assert v.worst_error == 0
+        assert v.errors == [0] * (len(offs) - 1)
+        assert v.counts == [[w.n for w in want]]
+    # a broken segment shows up in the worst error and in this rank's per-segment errors
+    bad = data.copy()
+    bad[offs[1] + 10] = 0x22  # unbalances the quotes of segment 1
+    wbad = oracle.stage1(bad[offs[1] : offs[2]], impl="fast")
+    if wbad.error != 0:
+        v = drv.run(torch.from_numpy(bad).cuda(), out)
+        assert v.worst_error == wbad.error
+        assert v.errors[1] == wbad.error and v.errors[0] == 0
