@@ -79,7 +79,10 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
 // kernel that follows resets it).  A static partition would be slightly cheaper but assumes that every CTA of the grid is
 // resident from the start: with another kernel on the device (the NCCL verdict exchange of the previous pass, a second
 // context) a displaced CTA would start only when some other CTA has finished its whole share, doubling the kernel time.
-constexpr uint32_t TICKET_CHUNKS = 4;
+#ifndef SJ_TICKET_CHUNKS
+#define SJ_TICKET_CHUNKS 4
+#endif
+constexpr uint32_t TICKET_CHUNKS = SJ_TICKET_CHUNKS;
 constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
 
 template <int NW, bool UTF8>

@@ -502,3 +502,43 @@ def test_ndjson_batch_driver_single_rank(dev):
         v = drv.run(torch.from_numpy(bad).cuda(), out)
         assert v.worst_error == wbad.error
         assert v.errors[1] == wbad.error and v.errors[0] == 0
+
+
+@pytest.mark.parametrize("kernel", ["auto", "persistent"])
+def test_maximum_length_document(kernel):
+    """len = 2^32 - 1, the largest document the uint32 index format allows (reference include/base.mojo:2): index values
+    above 2^31, chunk arithmetic at the top of the 32-bit range, trailer = len.  Built on the device, expected output
+    known in closed form (a 4 GiB oracle run would take minutes)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 << 30:
+        pytest.skip("needs ~10 GiB of device memory")
+    from mojo_simdjson_b200 import device
+
+    L = (1 << 32) - 1
+    ctx = device.Stage1Context(0, max_len=L)
+    try:
+        ctx.set_kernel(kernel)
+        buf = torch.full((L,), 0x20, dtype=torch.uint8, device="cuda")
+        buf[0] = ord("[")
+        buf[L - 1] = ord("]")
+        # a little structure at chosen offsets: `"k":1,` (6 bytes) -> structurals at +0 (quote), +3 (:), +4 (1), +5 (,)
+        spots = [1, 2047, 2048 * 3 - 2, (1 << 31) - 3, (1 << 31) + 5, (3 << 30) + 2045, L - 4096 - 7, L - 8]
+        pat = torch.tensor(list(b'"k":1,'), dtype=torch.uint8, device="cuda")
+        want = [0]
+        for p in spots:
+            buf[p : p + 6] = pat
+            want += [p, p + 3, p + 4, p + 5]
+        want.append(L - 1)
+        # one long string across many chunks near the top: its inside must contribute nothing
+        s0, s1 = (7 << 29) + 11, (7 << 29) + 11 + 5_000_000
+        buf[s0 + 1 : s1] = ord("{")
+        buf[s0] = ord('"')
+        buf[s1] = ord('"')
+        want = sorted(want + [s0])
+        out = torch.full((4096,), -1, dtype=torch.int32, device="cuda")
+        res = ctx.index(buf, out)
+        assert res.error == 0 and res.n == len(want)
+        got = out[: len(want) + 3].cpu().numpy().view(np.uint32).astype(np.int64).tolist()
+        assert got == want + [L, L, 0]
+    finally:
+        ctx.close()
