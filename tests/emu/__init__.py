@@ -22,6 +22,9 @@ def lib():
         L.emu_stage1.restype = C.c_int32
         L.emu_stage1.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64,
                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_uint32]
+        L.emu_stage1_stream.restype = C.c_int32
+        L.emu_stage1_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint32]
         L.emu_bitplanes32.restype = None
         L.emu_bitplanes32.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
@@ -43,3 +46,22 @@ def stage1(data: bytes, mis: int = 0, warps: int = 8, flags: int = 0, cap=None):
     assigned = n.value != 0xFFFFFFFF
     keep = min(int(nw.value) + (3 if assigned else 0), cap)
     return err, (n.value if assigned else None), int(nw.value), out[:keep].copy(), int(u8.value)
+
+
+def stage1_stream(data: bytes, mis: int = 0, flags: int = 0, cap=None):
+    """The stream pipeline's arithmetic on the host.  Returns (err, n, n_written, out, utf8, gave_up)."""
+    L = lib()
+    a = np.frombuffer(bytes(data), dtype=np.uint8)
+    n_bytes = int(a.size)
+    if cap is None:
+        cap = n_bytes + 3
+    out = np.full(max(cap, 1), 0xDEADBEEF, dtype=np.uint32)
+    n = C.c_uint32(0xFFFFFFFF)
+    nw = C.c_uint64(0)
+    u8 = C.c_int32(0)
+    spec = C.c_int32(0)
+    err = L.emu_stage1_stream(a.ctypes.data if n_bytes else None, n_bytes, mis, out.ctypes.data, cap,
+                              C.byref(n), C.byref(nw), C.byref(u8), C.byref(spec), flags)
+    assigned = n.value != 0xFFFFFFFF
+    keep = min(int(nw.value) + (3 if assigned else 0), cap)
+    return err, (n.value if assigned else None), int(nw.value), out[:keep].copy(), int(u8.value), bool(spec.value)

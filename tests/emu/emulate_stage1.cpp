@@ -310,3 +310,201 @@ extern "C" void emu_bitplanes32(const uint8_t *bytes32, uint32_t *planes8) {
     memcpy(w, bytes32, 32);
     bitplanes32(w, planes8);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stream pipeline (csrc/stage1_stream.cuh) on the host: per 2 KiB chunk the classify step with a 32-byte look-behind and
+// no other knowledge of what precedes it, the two mask planes and the chunk summary; then the ordered scan in the same
+// two levels as the kernels (blocks of 4096 summaries, block prefix, per-thread groups of 4 walked backwards); then the
+// flatten step driven only by the carry words.  *spec_out = 1 iff a chunk could not resolve its escape carry locally
+// (the GPU then hands the document to the persistent kernel); the output is unspecified in that case.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct Summary {
+    uint32_t c0, c1, flags;
+};
+SpanAcc span_of(const Summary &s) {
+    SpanAcc a;
+    a.par = s.flags & 1u;
+    a.c[0] = s.c0;
+    a.c[1] = s.c1;
+    a.un[0] = (s.flags >> 1) & 1u;
+    a.un[1] = (s.flags >> 2) & 1u;
+    a.u8 = (s.flags >> 3) & 1u;
+    return a;
+}
+}  // namespace
+
+extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t mis, uint32_t *out, uint64_t cap, uint32_t *n_out,
+                                     uint64_t *n_written_out, int32_t *utf8_err_out, int32_t *spec_out, uint32_t flags) {
+    if (spec_out) *spec_out = 0;
+    if (len == 0) return 13;
+    const int64_t alen = (int64_t)mis + (int64_t)len;
+    const int64_t nchunks = (alen + 2047) / 2048;
+    std::vector<uint8_t> mem((size_t)(nchunks * 2048 + 64));
+    for (size_t i = 0; i < mem.size(); i++) mem[i] = (i & 1) ? 0x5C : 0xF4;  // hostile bytes around the document
+    memcpy(mem.data() + mis, buf, (size_t)len);
+    const int64_t last = nchunks - 1;
+    const int64_t last_bytes = alen - last * 2048;
+
+    std::vector<uint64_t> plane0((size_t)nchunks * 32), plane1((size_t)nchunks * 32);
+    std::vector<Summary> sum((size_t)nchunks);
+    std::vector<uint8_t> stage(32 + 2048);
+    bool gave_up = false;
+    for (int64_t c = 0; c < nchunks; c++) {
+        // what the bulk copy brings: the chunk (the last one rounded up to 16 bytes) and 32 bytes before it; the rest of the
+        // buffer is stale
+        for (size_t i = 0; i < stage.size(); i++) stage[i] = 0x5C;
+        const int64_t nb = c == last ? ((last_bytes + 15) & ~15ll) : 2048;
+        memcpy(stage.data() + 32, mem.data() + c * 2048, (size_t)nb);
+        if (c > 0) memcpy(stage.data(), mem.data() + c * 2048 - 32, 32);
+        const uint8_t *chunk = stage.data() + 32;
+        const bool edge = (c == 0) || (c == last && last_bytes < 2048);
+        PrevState wst = {0, 0, 0};
+        if (c > 0) {
+            uint32_t bsm = 0;
+            for (int l = 0; l < 32; l++) bsm |= (uint32_t)(chunk[-1 - l] == 0x5C) << l;
+            wst = prev_state(bsm, 32, chunk[-1]);
+        }
+        if (wst.unresolved) gave_up = true;
+        Lane L[32];
+        uint32_t A = 0, O = 0;
+        for (int l = 0; l < 32; l++) {
+            Lane &ln = L[l];
+            const int64_t g0 = c * 2048 + (int64_t)l * 64;
+            uint32_t words[16], prev;
+            memcpy(words, chunk + l * 64, 64);
+            memcpy(&prev, chunk + l * 64 - 4, 4);
+            bool ends = false;
+            if (edge) {
+                ends = g0 + 64 == alen;
+                for (int k = 0; k < 16; k++) words[k] = mask_word(words[k], g0 + 4 * k, mis, alen);
+                prev = (g0 == 0) ? 0x20202020u : mask_word(prev, g0 - 4, mis, alen);
+            }
+            uint32_t pl[8], ph[8];
+            bitplanes32(words, pl);
+            bitplanes32(words + 8, ph);
+            Classes32 cl, ch;
+            classify_json32(pl, cl);
+            classify_json32(ph, ch);
+            ln.m.bs = join64(cl.bs, ch.bs);
+            ln.m.rq = join64(cl.rq, ch.rq);
+            ln.m.op = join64(cl.op, ch.op);
+            ln.m.ws = join64(cl.ws, ch.ws);
+            ln.m.ctl = join64(cl.ctl, ch.ctl);
+            ln.u8err = 0;
+            ln.c0 = ((pl[7] | ph[7]) != 0) || ((prev & 0x80808080u) != 0);  // any_hi (kept in c0 until the ballot below)
+            ln.c1 = prev;
+            ln.rel = ends;
+            memcpy(&ln.d, pl, 0);  // (planes are recomputed below when needed)
+            A |= (uint32_t)lane_all_backslash(ln.m.bs) << l;
+            O |= lane_trailing_run_parity(ln.m.bs) << l;
+        }
+        bool any_hi = false;
+        for (int l = 0; l < 32; l++) any_hi |= L[l].c0 != 0;
+        if (any_hi) {  // the whole warp takes the UTF-8 path or none of it does
+            for (int l = 0; l < 32; l++) {
+                const int64_t g0 = c * 2048 + (int64_t)l * 64;
+                uint32_t words[16];
+                memcpy(words, chunk + l * 64, 64);
+                if (edge)
+                    for (int k = 0; k < 16; k++) words[k] = mask_word(words[k], g0 + 4 * k, mis, alen);
+                uint32_t pl[8], ph[8];
+                bitplanes32(words, pl);
+                bitplanes32(words + 8, ph);
+                Utf8Pre32 ul, uh;
+                utf8_pre32(pl, ul);
+                utf8_pre32(ph, uh);
+                const Utf8Carry uc = utf8_carry_from_prev_word(L[l].c1);
+                uint32_t tail_must;
+                const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
+                L[l].u8err = (ue != 0) || (L[l].rel && tail_must != 0);
+            }
+        }
+        uint32_t PB = 0, NQ = 0;
+        for (int l = 0; l < 32; l++) {
+            L[l].q = lane_quotes(L[l].m, warp_lane_e_in(A, O, l, wst.e));
+            PB |= (uint32_t)(L[l].q.ps >> 63) << l;
+            NQ |= (uint32_t)(L[l].q.nqs >> 63) << l;
+        }
+        uint32_t fl = 0, wc0 = 0, wc1 = 0;
+        for (int l = 0; l < 32; l++) {
+            const uint32_t rel = (uint32_t)popc32(PB & ((1u << l) - 1u)) & 1u;
+            const uint32_t p_in = l ? ((NQ >> (l - 1)) & 1u) : wst.p;
+            const LaneDual d = lane_structurals_dual(L[l].m, L[l].q, rel, p_in);
+            plane0[(size_t)c * 32 + l] = d.m0;
+            plane1[(size_t)c * 32 + l] = d.m1;
+            wc0 += (uint32_t)popc64(d.m0);
+            wc1 += (uint32_t)popc64(d.m1);
+            fl |= (d.u0 << 1) | (d.u1 << 2) | (L[l].u8err << 3);
+        }
+        sum[(size_t)c] = {wc0, wc1, fl | ((uint32_t)popc32(PB) & 1u)};
+    }
+    if (gave_up) {
+        if (spec_out) *spec_out = 1;
+        return 0;
+    }
+    // ---- span_reduce: one aggregate per block of 4096 summaries ----
+    const int64_t BLOCK = 4096, PER_THREAD = 4;
+    const int64_t nblocks = (nchunks + BLOCK - 1) / BLOCK;
+    std::vector<SpanAcc> block((size_t)nblocks);
+    for (int64_t b = 0; b < nblocks; b++) {
+        SpanAcc acc = span_empty();
+        for (int64_t c = b * BLOCK; c < nchunks && c < (b + 1) * BLOCK; c++) acc = span_concat(acc, span_of(sum[(size_t)c]));
+        block[(size_t)b] = acc;
+    }
+    // ---- span_carries: block prefix, inclusive span per thread group, backwards walk ----
+    std::vector<uint64_t> carry((size_t)nchunks);
+    TilePrefix fin = {0, 0, 0, 0, 0};
+    for (int64_t b = 0; b < nblocks; b++) {
+        SpanAcc before = span_empty();
+        for (int64_t j = 0; j < b; j++) before = span_concat(before, block[(size_t)j]);
+        SpanAcc run = before;
+        for (int64_t c0 = b * BLOCK; c0 < nchunks && c0 < (b + 1) * BLOCK; c0 += PER_THREAD) {
+            Summary s4[4] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int k = 0; k < PER_THREAD; k++)
+                if (c0 + k < nchunks) s4[k] = sum[(size_t)(c0 + k)];
+            for (int k = 0; k < PER_THREAD; k++) run = span_concat(run, span_of(s4[k]));  // inclusive span of this "thread"
+            uint32_t par = run.par & 1u, cnt = run.c[0];
+            if (c0 < nchunks && c0 + PER_THREAD >= nchunks) {
+                fin.s_out = par;
+                fin.err = (run.un[0] ? EF_UNESCAPED : 0u) | (run.u8 ? EF_UTF8 : 0u);
+                fin.count = cnt;
+            }
+            for (int k = PER_THREAD - 1; k >= 0; k--) {
+                const uint32_t s_in = (par ^ s4[k].flags) & 1u;
+                cnt -= s_in ? s4[k].c1 : s4[k].c0;
+                par = s_in;
+                if (c0 + k < nchunks) carry[(size_t)(c0 + k)] = (uint64_t)cnt | (s_in ? (1ull << 63) : 0ull);
+            }
+        }
+    }
+    // ---- flatten: only the carry word and the chosen plane ----
+    for (int64_t c = 0; c < nchunks; c++) {
+        const uint64_t cw = carry[(size_t)c];
+        const bool inside = (cw >> 63) != 0;
+        uint64_t o = cw & ((1ull << 40) - 1);
+        for (int l = 0; l < 32; l++) {
+            uint64_t st = inside ? plane1[(size_t)c * 32 + l] : plane0[(size_t)c * 32 + l];
+            const uint32_t v0 = (uint32_t)c * 2048u + (uint32_t)l * 64u - mis;
+            while (st) {
+                const int bit = __builtin_ctzll(st);
+                st &= st - 1;
+                if (o < cap) out[o] = v0 + (uint32_t)bit;
+                o++;
+            }
+        }
+    }
+    const uint64_t n = fin.count;
+    if (n_written_out) *n_written_out = n;
+    if (utf8_err_out) *utf8_err_out = (fin.err & EF_UTF8) ? 1 : 0;
+    if (fin.s_out) return 15;
+    if (fin.err & EF_UNESCAPED) return 14;
+    if (n + 3 > cap) return 1;
+    if (n_out) *n_out = (uint32_t)n;
+    out[n] = (uint32_t)len;
+    out[n + 1] = (uint32_t)len;
+    out[n + 2] = 0;
+    if (n == 0) return 13;
+    if ((flags & 1u) && (fin.err & EF_UTF8)) return 11;
+    return 0;
+}

@@ -65,3 +65,65 @@ def test_fuzz_nasty(xs, mis):
 @given(st.binary(min_size=1, max_size=5000), st.integers(0, 15))
 def test_fuzz_binary(data, mis):
     _check(data, mis, 2, flags=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# stream pipeline (stage1_stream.cuh): chunk summaries -> two-level span scan -> carry words -> flatten
+# ------------------------------------------------------------------------------------------------
+def _must_give_up(data: bytes, mis: int) -> bool:
+    """The speculation fails exactly when the 32 bytes before some 2 KiB chunk boundary (aligned coordinates) cannot decide
+    the carries: all backslashes (is the chunk's first byte escaped?), or a quote preceded by 31 backslashes (is that
+    quote escaped, i.e. is the previous byte a scalar?)."""
+    a = bytes(mis) + bytes(data)  # chunk 0 has no look-behind, and 2048 - 32 > mis: the window is always document bytes
+    for b in range(2048, len(a), 2048):
+        w = a[b - 32 : b]
+        if w == b"\\" * 32 or w == b"\\" * 31 + b'"':
+            return True
+    return False
+
+
+def _check_stream(data: bytes, mis: int, flags: int = 0):
+    want = oracle.stage1(data, flags=flags, impl="fast" if len(data) > 20000 else "ref")
+    err, n, nw, idx, u8, gave_up = emu.stage1_stream(data, mis=mis, flags=flags)
+    if not data:
+        assert err == want.error
+        return False
+    # mis < 16 and chunk boundaries are multiples of 2048 >= 2048: the look-behind always lies inside the document or
+    # covers document bytes only
+    assert gave_up == _must_give_up(data, mis)
+    if gave_up:
+        return True
+    assert err == want.error
+    assert n == want.n
+    assert nw == want.n_written
+    assert np.array_equal(idx, want.indexes)
+    assert u8 == want.utf8_error
+    return False
+
+
+def test_stream_pipeline_adversarial_corpus():
+    gave_up = 0
+    for name, data in cases.adversarial_cases(tile_bytes=(2048, 4096, 16384)):
+        for mis in (0, 5):
+            try:
+                gave_up += _check_stream(data, mis)
+                _check_stream(data, mis, flags=1)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"case {name} mis={mis}") from e
+    assert gave_up > 0, "the corpus must contain inputs that defeat the speculation (long backslash runs at chunk ends)"
+
+
+def test_stream_pipeline_many_blocks():
+    """More than one block of 4096 chunk summaries (> 8 MiB), with strings that stay open across block boundaries."""
+    unit = b'{"a":[1,2,{"b":"' + b"x" * 3000 + b'\\"y"}],"c":"\xe2\x82\xac"},'
+    data = b"[" + unit * ((20 << 20) // len(unit)) + b'"' + b"s" * (9 << 20) + b'",0]'
+    assert len(data) > 3 * 4096 * 2048
+    _check_stream(data, 0)
+    _check_stream(data, 7)
+    _check_stream(data[:-5], 3)  # unclosed
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.sampled_from(list(cases.NASTY)), min_size=1, max_size=9000), st.integers(0, 15))
+def test_stream_pipeline_fuzz_nasty(xs, mis):
+    _check_stream(bytes(xs), mis)
