@@ -373,7 +373,11 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 Utf8Pre32 ul, uh;
                 utf8_pre32(pl, ul);
                 utf8_pre32(ph, uh);
-                const Utf8Carry uc = utf8_carry_from_prev_word(in.prev);
+                // what the three bytes before this lane's 64 demand of its first bytes: nothing unless one of them is a lead
+                // byte (>= 0xC0), i.e. a multi-byte character straddles a lane boundary somewhere in the warp
+                Utf8Carry uc = {0, 0, 0, 0};
+                const bool straddle = (in.prev & (in.prev << 1) & 0x80808000u) != 0;
+                if (__any_sync(0xFFFFFFFFu, straddle)) uc = utf8_carry_from_prev_word(in.prev);
                 uint32_t tail_must;
                 const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
                 u8err = (ue != 0) || (in.ends && tail_must != 0);
