@@ -68,6 +68,7 @@ struct sjb200_ctx {
     uint64_t *d_carry = nullptr;           //             one carry word per chunk
     uint64_t split_chunks = 0;             //             chunks the two arrays hold (allocated on first use)
     bool scratch_failed = false;           //             that allocation failed once: automatic choice stays with the fused kernel
+    uint4 *d_u8_slots = nullptr;           // stream pipeline: parked bit planes of lanes whose UTF-8 validation is deferred
     uint32_t *d_chunk_sum = nullptr;       // stream pipeline: per-chunk and per-1024-chunk summaries, speculation flag
     uint32_t *d_block_sum = nullptr;
     uint32_t *d_spec_flag = nullptr;
@@ -203,6 +204,10 @@ cudaError_t launch_stream(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     cudaError_t e = cudaGetLastError();
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     const bool pdl = use_pdl();
+    if (e == cudaSuccess && UTF8) {   // the lanes whose UTF-8 validation the classify kernel deferred
+        const unsigned u8_ctas = (nchunks * U8_SLOTS + 255) / 256;
+        e = launch_dependent(stage1_utf8_lanes_kernel, u8_ctas, 256, 0, s, pdl, p, nchunks);
+    }
     if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     constexpr int FW = 8;
@@ -276,6 +281,8 @@ void free_split_scratch(sjb200_ctx *c) {
     cudaFree(c->d_chunk_sum);
     cudaFree(c->d_block_sum);
     cudaFree(c->d_spec_flag);
+    cudaFree(c->d_u8_slots);
+    c->d_u8_slots = nullptr;
     c->d_masks = c->d_carry = nullptr;
     c->d_chunk_sum = c->d_block_sum = c->d_spec_flag = nullptr;
     c->split_chunks = 0;
@@ -342,6 +349,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     p.chunk_sum = nullptr;
     p.block_sum = nullptr;
     p.spec_flag = nullptr;
+    p.u8_slots = nullptr;
     if (d.split || d.stream) {
         const uint64_t chunks = ntiles * (uint64_t)d.warps;
         if (chunks > c->split_chunks) {  // first use (or a larger document than before): (re)allocate, stream ordered
@@ -351,7 +359,8 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
             const uint64_t n = chunks > want ? chunks : want;
             if (cudaMalloc(&c->d_masks, n * 512) != cudaSuccess || cudaMalloc(&c->d_carry, n * 8) != cudaSuccess ||
                 cudaMalloc(&c->d_chunk_sum, n * 16) != cudaSuccess || cudaMalloc(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16) != cudaSuccess ||
-                cudaMalloc(&c->d_spec_flag, 256) != cudaSuccess || cudaMemset(c->d_spec_flag, 0, 256) != cudaSuccess) {
+                cudaMalloc(&c->d_spec_flag, 256) != cudaSuccess || cudaMemset(c->d_spec_flag, 0, 256) != cudaSuccess ||
+                cudaMalloc(&c->d_u8_slots, n * (size_t)(U8_SLOTS * U8_SLOT_VECTORS * 16)) != cudaSuccess) {
                 free_split_scratch(c);
                 cudaGetLastError();
                 if (!auto_kind) return SJB200_MEMALLOC;   // the caller asked for this organisation explicitly
@@ -374,6 +383,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
             p.chunk_sum = c->d_chunk_sum;
             p.block_sum = c->d_block_sum;
             p.spec_flag = c->d_spec_flag;
+            p.u8_slots = c->d_u8_slots;
         }
     }
     return SJB200_SUCCESS;
@@ -394,7 +404,7 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     if (d.stream && whole) {
         // speculative pipeline, then the persistent kernel as its exact fallback (returns at once unless the flag was raised)
         e = utf8 ? launch_stream<true>(p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(p, stream, c->sm_count * c->stream_occ);
-        c->launches += 4;
+        c->launches += utf8 ? 5 : 4;
     }
     if (d.stream && whole && e != cudaSuccess) {
         return cuda_err(e);

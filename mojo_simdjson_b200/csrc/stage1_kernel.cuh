@@ -105,6 +105,7 @@ struct Stage1Params {
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
     uint64_t *masks;        // split pair only: [chunk][parity][lane] structural masks, 512 bytes per 2 KiB chunk
     uint64_t *carry;        // split pair only: per chunk, bit 63 = starts inside a string, bits 0..39 = rank of its first index
+    uint4 *u8_slots;        // stream pipeline only: per chunk 8 slots x 5 x 16 B for lanes whose UTF-8 validation is deferred
     uint32_t *chunk_sum;    // stream pipeline only: 16 bytes per chunk {count0, count1, flags, 0}
     uint32_t *block_sum;    // stream pipeline only: the same per 1024 chunks
     uint32_t *spec_flag;    // stream pipeline: == gen once a chunk could not resolve its escape carry locally.  Persistent
@@ -316,6 +317,7 @@ struct LanePhase1 {
     uint32_t wc0, wc1;
     uint32_t wflags;  // bit0 quote parity, bit1/2 unescaped control (outside/inside), bit3 UTF-8 violation
     uint32_t tail;    // bit0 e_out, bit1 p_out after the warp's last byte
+    uint32_t u8_lanes;  // stream pipeline: lanes whose UTF-8 validation is left to stage1_utf8_lanes_kernel (else 0)
 };
 
 // every shared-memory read of the input happens here (the persistent kernel frees the buffer right after)
@@ -349,10 +351,18 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
                        : warp_prev_state(smem_tile, woff, lane, tb, (int64_t)P.mis, alen, edge, tile, P.desc, P.gen);
 }
 
-template <bool UTF8>
-__device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P) {
+// DEFER_U8: when only a few lanes of the warp hold (or directly follow) bytes >= 0x80, do not validate UTF-8 here -- the
+// whole warp would pay ~75 ALU instructions for them -- but report those lanes; stage1_utf8_lanes_kernel (stage1_stream.cuh)
+// validates exactly those lanes, 32 of them per warp.
+#ifndef SJ_U8_DEFER_MAX
+#define SJ_U8_DEFER_MAX 8
+#endif
+template <bool UTF8, bool DEFER_U8 = false>
+__device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P,
+                                             uint4 *u8_slots = nullptr /* DEFER_U8: this chunk's 8 slots of 5 uint4 */) {
     LaneMasks m;
     uint32_t u8err = 0;
+    r.u8_lanes = 0;
     {
         uint32_t pl[8], ph[8];
         bitplanes32(in.w, pl);
@@ -369,7 +379,20 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
             // whole-warp fast path: nothing >= 0x80 in these 2 KiB nor in the 4 bytes before each lane's 64 (the lead /
             // continuation classes are not even computed then)
             const bool any_hi = ((pl[7] | ph[7]) != 0) || ((in.prev & 0x80808080u) != 0);
-            if (__any_sync(0xFFFFFFFFu, any_hi)) {
+            const uint32_t hi_lanes = __ballot_sync(0xFFFFFFFFu, any_hi);
+            r.u8_lanes = 0;
+            if (DEFER_U8 && __popc(hi_lanes) <= SJ_U8_DEFER_MAX) {
+                // the k-th flagged lane parks its bit planes, the 4 bytes before it and its end-of-document bit in slot k
+                r.u8_lanes = hi_lanes;
+                if (any_hi) {
+                    uint4 *s = u8_slots + 5 * __popc(hi_lanes & ((1u << lane) - 1u));   // 80 contiguous bytes per slot
+                    __stcs(s + 0, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+                    __stcs(s + 1, make_uint4(pl[4], pl[5], pl[6], pl[7]));
+                    __stcs(s + 2, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                    __stcs(s + 3, make_uint4(ph[4], ph[5], ph[6], ph[7]));
+                    __stcs(s + 4, make_uint4(in.prev, in.ends, 0u, 0u));
+                }
+            } else if (hi_lanes) {
                 Utf8Pre32 ul, uh;
                 utf8_pre32(pl, ul);
                 utf8_pre32(ph, uh);

@@ -157,17 +157,51 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
                 fetch(b);
                 if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
             }
-            warp_compute<UTF8>(ph, in, lane, P);
+            warp_compute<UTF8, true>(ph, in, lane, P, P.u8_slots + (size_t)c * (8 * 5));
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
         __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
         __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
-        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
+        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, ph.u8_lanes);
         if (++b == DEPTH) {
             b = 0;
             phase ^= 1u;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UTF-8 validation of the lanes the classify kernel deferred.  Chunk c owns 8 slots of 5 x 16 bytes in P.u8_slots
+// ([chunk][slot 0..7][vector 0..4]); the first popc(summary word 3) of them hold, for the chunk's flagged lanes in lane
+// order, the 16 bit-plane words, the 4 bytes before the lane and its end-of-document bit.  One thread per slot.  A
+// violation stores the document generation into spec_flag[1]; span_carries folds it into the verdict.
+// ---------------------------------------------------------------------------------------------
+constexpr int U8_SLOTS = 8;           // == SJ_U8_DEFER_MAX
+constexpr int U8_SLOT_VECTORS = 5;
+static_assert(U8_SLOTS == SJ_U8_DEFER_MAX, "slot count and deferral limit must agree");
+
+__global__ void __launch_bounds__(256) stage1_utf8_lanes_kernel(const Stage1Params P, uint32_t nchunks) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t c = t / U8_SLOTS, slot = t % U8_SLOTS;
+    grid_dependency_wait();
+    bool bad = false;
+    if (c < nchunks) {
+        const uint32_t lanes = __ldcg(P.chunk_sum + (size_t)c * 4 + 3);
+        if (slot < (uint32_t)__popc(lanes)) {
+            const uint4 *s = P.u8_slots + ((size_t)c * U8_SLOTS + slot) * U8_SLOT_VECTORS;
+            const uint4 a = __ldcs(s), b = __ldcs(s + 1), d = __ldcs(s + 2), e = __ldcs(s + 3), f = __ldcs(s + 4);
+            const uint32_t pl[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const uint32_t ph[8] = {d.x, d.y, d.z, d.w, e.x, e.y, e.z, e.w};
+            Utf8Pre32 ul, uh;
+            utf8_pre32(pl, ul);
+            utf8_pre32(ph, uh);
+            const Utf8Carry uc = utf8_carry_from_prev_word(f.x);
+            uint32_t tail_must;
+            const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
+            bad = (ue != 0) || (f.y != 0 && tail_must != 0);
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) P.spec_flag[1] = P.gen;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,7 +304,8 @@ __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1P
         pre.s_out = par;
         pre.e_out = 0;
         pre.p_out = 0;
-        pre.err = (un ? EF_UNESCAPED : 0u) | (u8 ? EF_UTF8 : 0u);
+        const uint32_t u8_deferred = __ldcg(P.spec_flag + 1) == P.gen;   // stage1_utf8_lanes_kernel found a violation
+        pre.err = (un ? EF_UNESCAPED : 0u) | ((u8 | u8_deferred) ? EF_UTF8 : 0u);
         pre.count = cnt;
         write_verdict(P, pre);
     }

@@ -348,6 +348,8 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
 
     std::vector<uint64_t> plane0((size_t)nchunks * 32), plane1((size_t)nchunks * 32);
     std::vector<Summary> sum((size_t)nchunks);
+    std::vector<uint32_t> deferred((size_t)nchunks, 0u);
+    std::vector<uint32_t> slots((size_t)nchunks * 8 * 18, 0xA5A5A5A5u);  // parked {planes[16], prev, ends} of deferred lanes
     std::vector<uint8_t> stage(32 + 2048);
     bool gave_up = false;
     for (int64_t c = 0; c < nchunks; c++) {
@@ -399,9 +401,25 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
             A |= (uint32_t)lane_all_backslash(ln.m.bs) << l;
             O |= lane_trailing_run_parity(ln.m.bs) << l;
         }
-        bool any_hi = false;
-        for (int l = 0; l < 32; l++) any_hi |= L[l].c0 != 0;
-        if (any_hi) {  // the whole warp takes the UTF-8 path or none of it does
+        uint32_t hi_lanes = 0;
+        for (int l = 0; l < 32; l++) hi_lanes |= (uint32_t)(L[l].c0 != 0) << l;
+        if (popc32(hi_lanes) <= 8) {
+            deferred[(size_t)c] = hi_lanes;  // few lanes: parked for the second pass below (stage1_utf8_lanes_kernel)
+            int rank = 0;
+            for (int l = 0; l < 32; l++) {
+                if (!((hi_lanes >> l) & 1u)) continue;
+                const int64_t g0 = c * 2048 + (int64_t)l * 64;
+                uint32_t words[16];
+                memcpy(words, chunk + l * 64, 64);
+                if (edge)
+                    for (int k = 0; k < 16; k++) words[k] = mask_word(words[k], g0 + 4 * k, mis, alen);
+                uint32_t *sl = slots.data() + ((size_t)c * 8 + rank++) * 18;
+                bitplanes32(words, sl);
+                bitplanes32(words + 8, sl + 8);
+                sl[16] = L[l].c1;   // prev (already masked)
+                sl[17] = L[l].rel;  // the document ends with this lane
+            }
+        } else {  // the whole warp takes the UTF-8 path
             for (int l = 0; l < 32; l++) {
                 const int64_t g0 = c * 2048 + (int64_t)l * 64;
                 uint32_t words[16];
@@ -443,6 +461,21 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
         if (spec_out) *spec_out = 1;
         return 0;
     }
+    // ---- stage1_utf8_lanes_kernel: one "thread" per parked slot ----
+    bool u8_deferred_bad = false;
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int cnt = popc32(deferred[(size_t)c]);
+        for (int slot = 0; slot < cnt; slot++) {
+            const uint32_t *sl = slots.data() + ((size_t)c * 8 + slot) * 18;
+            Utf8Pre32 ul, uh;
+            utf8_pre32(sl, ul);
+            utf8_pre32(sl + 8, uh);
+            const Utf8Carry uc = utf8_carry_from_prev_word(sl[16]);
+            uint32_t tail_must;
+            const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
+            if (ue != 0 || (sl[17] != 0 && tail_must != 0)) u8_deferred_bad = true;
+        }
+    }
     // ---- span_reduce: one aggregate per block of 4096 summaries ----
     const int64_t BLOCK = 4096, PER_THREAD = 4;
     const int64_t nblocks = (nchunks + BLOCK - 1) / BLOCK;
@@ -467,7 +500,7 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
             uint32_t par = run.par & 1u, cnt = run.c[0];
             if (c0 < nchunks && c0 + PER_THREAD >= nchunks) {
                 fin.s_out = par;
-                fin.err = (run.un[0] ? EF_UNESCAPED : 0u) | (run.u8 ? EF_UTF8 : 0u);
+                fin.err = (run.un[0] ? EF_UNESCAPED : 0u) | ((run.u8 || u8_deferred_bad) ? EF_UTF8 : 0u);
                 fin.count = cnt;
             }
             for (int k = PER_THREAD - 1; k >= 0; k--) {

@@ -542,3 +542,29 @@ def test_maximum_length_document(kernel):
         assert got == want + [L, L, 0]
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("kernel", ["stream", "persistent"])
+def test_utf8_verdicts_sparse_lanes(dev, scratch, kernel):
+    """Valid and invalid UTF-8 sequences in otherwise ASCII documents, placed so that they straddle lane (64 B) and chunk
+    (2 KiB) boundaries, sit at the very start / end of the document, or follow a lane that is pure ASCII: in the stream
+    pipeline these are exactly the lanes whose validation is deferred to stage1_utf8_lanes_kernel."""
+    seqs = list(cases.UTF8_VALID) + list(cases.UTF8_INVALID)
+    for k, seq in enumerate(seqs):
+        seq = seq if isinstance(seq, (bytes, bytearray)) else seq.encode("utf-8", "surrogatepass")
+        for pos in (0, 1, 60, 62, 63, 64, 2044, 2046, 2047, 2048, 4095, 6000):
+            body = bytearray(b"a" * 7000)
+            body[pos:pos] = seq
+            for data in (b'"' + bytes(body) + b'"', b'"' + bytes(body[: pos + len(seq)])):  # second one: ends right after the sequence
+                want = oracle.stage1(data, flags=1, impl="ref")
+                res, out = run_device(dev, scratch, data, flags=1, kernel=kernel, warps=8, mis=(k + pos) % 16)
+                try:
+                    assert_same(res, out, want)
+                except AssertionError as e:  # pragma: no cover
+                    raise AssertionError(f"seq={seq!r} pos={pos} len={len(data)} kernel={kernel}") from e
+    # many flagged lanes in one chunk (more than the deferral limit) next to chunks with a single one
+    data = b'["' + ("é" * 40 + "a" * 200).encode() * 30 + b'", "' + b"a" * 3000 + "€".encode() + b"a" * 3000 + b'\xc3"]'
+    want = oracle.stage1(data, flags=1, impl="ref")
+    res, out = run_device(dev, scratch, data, flags=1, kernel=kernel, warps=8)
+    assert_same(res, out, want)
+    assert want.utf8_error == 1
