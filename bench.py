@@ -379,8 +379,9 @@ def run_ours(args):
     kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (160 << 20) else ("split" if seg >= (48 << 20) else "persistent"))
     prof = ncu_traffic(kind)
     if kind == "stream":
-        kname = ("stage-1 stream pipeline, 5 launches per document: stage1_stream_classify_kernel -> stage1_span_reduce_kernel -> "
-                 "stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)")
+        kname = ("stage-1 stream pipeline, 6 launches per document: stage1_stream_classify_kernel -> stage1_utf8_lanes_kernel -> "
+                 "stage1_span_reduce_kernel -> stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a "
+                 "no-op fallback)")
     else:
         kname = {"persistent": "stage1_persistent_kernel", "dataflow": "stage1_dataflow_kernel", "tile": "stage1_kernel",
                  "split": "stage1_classify_kernel + stage1_flatten_kernel"}[kind]

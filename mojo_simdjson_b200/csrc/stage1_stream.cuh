@@ -1,20 +1,23 @@
-// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of four stream-ordered launches with no
-// waiting between warps, CTAs or launches other than stream order:
+// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of five stream-ordered launches with no
+// waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them):
 //
 //   stream_classify : every warp is its own pipeline.  A warp draws runs of 4 consecutive 2 KiB chunks from an atomic
 //                     counter, each chunk fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
 //                     mbarrier each) together with the 32 bytes before it, which decide the escape / scalar carries
 //                     entering the chunk.  Output per chunk: the two structural mask planes (string state entering the
-//                     chunk unknown -> one plane per parity) and a 16-byte summary {count0, count1, flags}.
-//   span_reduce     : 1024 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
+//                     chunk unknown -> one plane per parity), a 16-byte summary {count0, count1, flags, deferred lanes}
+//                     and, for at most 8 lanes with bytes >= 0x80, their parked bit planes.
+//   utf8_lanes      : UTF-8 validation of the parked lanes, one thread per lane (instead of one warp per lane).
+//   span_reduce     : 4096 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
 //   span_carries    : block prefix from the block aggregates, then the same local scan -> one carry word per chunk
 //                     (bit 63 = starts inside a string, bits 0..39 = rank of its first index) and the verdict.
 //   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
 //
-// The only carry stage 1 cannot resolve from a bounded look-behind is the escape state after a backslash run that covers
-// the whole 32-byte look-behind of a chunk.  A chunk that sees one raises `spec_flag` (stores the document generation);
-// the three later launches then do nothing and the persistent kernel, enqueued behind them with Stage1Params::spec_flag
-// set, redoes the document exactly.  Otherwise that kernel returns at once.  Results are identical either way.
+// The only carries stage 1 cannot resolve from a bounded look-behind are the escape state after a backslash run that
+// covers the whole 32-byte look-behind of a chunk and the scalar state after a quote preceded by 31 backslashes.  A chunk
+// that sees either raises `spec_flag` (stores the document generation); the later launches then do nothing and the
+// persistent kernel, enqueued behind them with Stage1Params::spec_flag set, redoes the document exactly.  Otherwise that
+// kernel returns at once.  Results are identical either way.
 // Reference: json_structural_indexer.mojo:83-186 (step / next / finish), restated in oracle/stage1_oracle.c.
 #pragma once
 #include "stage1_split.cuh"
