@@ -266,11 +266,12 @@ def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
         assert int((scratch.out[:shift] != -1).sum()) == 0
 
 
-def test_split_pair_capacity_and_flags(dev, scratch):
+@pytest.mark.parametrize("kernel", ["split", "stream"])
+def test_split_pair_capacity_and_flags(dev, scratch, kernel):
     data = b'[' + b'1,' * 40000 + b'1]'
     want = oracle.stage1(data, impl="fast")
     for cap in (want.n + 3, want.n + 2, want.n, 1000, 3):
-        res, out = run_device(dev, scratch, data, cap=cap, warps=8, kernel="split")
+        res, out = run_device(dev, scratch, data, cap=cap, warps=8, kernel=kernel)
         if cap >= want.n + 3:
             assert_same(res, out, want)
         else:
@@ -281,10 +282,10 @@ def test_split_pair_capacity_and_flags(dev, scratch):
     bad = b'["\xc0\x80", "' + b"x" * 70000 + b'"]'
     for flags in (0, 1):
         w = oracle.stage1(bad, flags=flags, impl="ref")
-        res, out = run_device(dev, scratch, bad, flags=flags, warps=16, kernel="split")
+        res, out = run_device(dev, scratch, bad, flags=flags, warps=16, kernel=kernel)
         assert_same(res, out, w)
         assert res.error == (11 if flags else 0)
-    res, out = run_device(dev, scratch, bad, flags=4, warps=16, kernel="split")
+    res, out = run_device(dev, scratch, bad, flags=4, warps=16, kernel=kernel)
     assert res.error == 0 and res.utf8_error == -1
 
 
