@@ -73,6 +73,8 @@ struct sjb200_ctx {
     uint32_t *d_block_sum = nullptr;
     uint32_t *d_spec_flag = nullptr;
     int stream_occ = 0;                    // resident CTAs per SM of the stream classify kernel
+    cudaStream_t aux_stream = nullptr;     // stream pipeline: the deferred UTF-8 lanes are validated here, beside the scan
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -195,24 +197,34 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
 #endif
 constexpr int STREAM_NW = SJ_STREAM_NW;
 template <bool UTF8>
-cudaError_t launch_stream(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = StreamCfg<STREAM_NW>;
     const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
     stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
     cudaError_t e = cudaGetLastError();
-    const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     const bool pdl = use_pdl();
-    if (e == cudaSuccess && UTF8) {   // the lanes whose UTF-8 validation the classify kernel deferred
+    if (e == cudaSuccess && UTF8) {
+        // The lanes whose UTF-8 validation the classify kernel deferred: on the context's second stream, beside the two
+        // (latency-bound) scan launches and the start of the flatten kernel.  Nothing on `s` needs its result before the
+        // last launch of the document, which folds a violation into the verdict (stage1_persistent.cuh).
         const unsigned u8_ctas = (nchunks * U8_SLOTS + 255) / 256;
-        e = launch_dependent(stage1_utf8_lanes_kernel, u8_ctas, 256, 0, s, pdl, p, nchunks);
+        e = cudaEventRecord(c->ev_fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
+        if (e == cudaSuccess) {
+            stage1_utf8_lanes_kernel<<<u8_ctas, 256, 0, c->aux_stream>>>(p, nchunks);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_join, c->aux_stream);
     }
+    const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     constexpr int FW = 8;
     if (e == cudaSuccess)
         e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
+    if (e == cudaSuccess && UTF8) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch
     return e;
 }
 cudaError_t prepare_stream(int *occ) {
@@ -403,7 +415,7 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     if (!(d.stream && whole)) p.spec_flag = nullptr;   // a partial range is indexed by the persistent kernel alone
     if (d.stream && whole) {
         // speculative pipeline, then the persistent kernel as its exact fallback (returns at once unless the flag was raised)
-        e = utf8 ? launch_stream<true>(p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(p, stream, c->sm_count * c->stream_occ);
+        e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(c, p, stream, c->sm_count * c->stream_occ);
         c->launches += utf8 ? 5 : 4;
     }
     if (d.stream && whole && e != cudaSuccess) {
@@ -558,6 +570,9 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
     if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
     if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -586,6 +601,9 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     for (int k = 0; k < sjb200_ctx::MAX_CHUNKS; k++)
         if (c->chunk_ev[k]) cudaEventDestroy(c->chunk_ev[k]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

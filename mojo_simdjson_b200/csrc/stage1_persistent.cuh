@@ -63,7 +63,19 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
     if (P.spec_flag && __ldg(P.spec_flag) != P.gen) {
         // launched as the exact fallback of the stream pipeline (stage1_stream.cuh) and not needed: only keep the
         // ticket-counter alternation intact
-        if (blockIdx.x == 0 && tid == 0) P.ticket[(P.ticket_sel + 1) & 1u] = 0;
+        if (blockIdx.x == 0 && tid == 0) {
+            P.ticket[(P.ticket_sel + 1) & 1u] = 0;
+            if (__ldcg(P.spec_flag + 1) == P.gen) {
+                // stage1_utf8_lanes_kernel found a violation among the lanes whose validation had been deferred: same
+                // place in the verdict as in write_verdict (after EMPTY, before SUCCESS; reference :185-186 slot)
+                Stage1Result *r = P.result;
+                r->utf8_error = 1;
+                if ((P.flags & 1u) && r->error == ERR_SUCCESS) {
+                    r->error = ERR_UTF8_ERROR;
+                    if (P.dev_status) P.dev_status[0] = ERR_UTF8_ERROR;
+                }
+            }
+        }
         return;
     }
     const uint32_t bar_in_full = smem_u32(&s_bar[0]), bar_in_empty = smem_u32(&s_bar[1]);

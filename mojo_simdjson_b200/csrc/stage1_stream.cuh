@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
 // UTF-8 validation of the lanes the classify kernel deferred.  Chunk c owns 8 slots of 5 x 16 bytes in P.u8_slots
 // ([chunk][slot 0..7][vector 0..4]); the first popc(summary word 3) of them hold, for the chunk's flagged lanes in lane
 // order, the 16 bit-plane words, the 4 bytes before the lane and its end-of-document bit.  One thread per slot.  A
-// violation stores the document generation into spec_flag[1]; span_carries folds it into the verdict.
+// violation stores the document generation into spec_flag[1]; the document's last launch (the persistent kernel in its
+// not-needed-as-fallback role) folds it into the verdict.  Runs on a second stream beside the scan and flatten launches.
 // ---------------------------------------------------------------------------------------------
 constexpr int U8_SLOTS = 8;           // == SJ_U8_DEFER_MAX
 constexpr int U8_SLOT_VECTORS = 5;
@@ -186,7 +187,6 @@ static_assert(U8_SLOTS == SJ_U8_DEFER_MAX, "slot count and deferral limit must a
 __global__ void __launch_bounds__(256) stage1_utf8_lanes_kernel(const Stage1Params P, uint32_t nchunks) {
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     const uint32_t c = t / U8_SLOTS, slot = t % U8_SLOTS;
-    grid_dependency_wait();
     bool bad = false;
     if (c < nchunks) {
         const uint32_t lanes = __ldcg(P.chunk_sum + (size_t)c * 4 + 3);
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1P
         pre.s_out = par;
         pre.e_out = 0;
         pre.p_out = 0;
-        const uint32_t u8_deferred = __ldcg(P.spec_flag + 1) == P.gen;   // stage1_utf8_lanes_kernel found a violation
-        pre.err = (un ? EF_UNESCAPED : 0u) | ((u8 | u8_deferred) ? EF_UTF8 : 0u);
+        // (a violation among the deferred UTF-8 lanes is folded in later, by the document's last launch)
+        pre.err = (un ? EF_UNESCAPED : 0u) | (u8 ? EF_UTF8 : 0u);
         pre.count = cnt;
         write_verdict(P, pre);
     }
