@@ -86,12 +86,15 @@ int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
  *   TILE        one tile per CTA, look-back by warp 0
  *   PERSISTENT  persistent CTAs, compute warps + scan warp, classify and flatten fused
  *   DATAFLOW    persistent CTAs, classifier warps -> mask ring in shared memory -> flattener warps
- *   SPLIT       two launches: classify (masks + per-chunk carries to HBM), then flatten; needs len/4 bytes of scratch,
- *               allocated on first use (MEMALLOC if that fails)
+ *   SPLIT       two launches: classify (masks + per-chunk carries to HBM), then flatten.  Scratch for SPLIT and STREAM is
+ *               allocated on first use, once, for the context's max_len: 0.57 * max_len bytes (mask planes max_len/4,
+ *               parked UTF-8 lanes 0.31 * max_len, summaries).  If that fails an explicit choice returns MEMALLOC, the
+ *               automatic choice stays with PERSISTENT, which needs none
  *   STREAM      four launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp, two tiny
  *               scan kernels over the chunk summaries, flatten; speculates that no backslash run covers a chunk's whole
- *               32-byte look-behind and, when one does, re-runs the document with PERSISTENT (same results).  Scratch as
- *               for SPLIT.  Whole documents only: the chunked host path uses PERSISTENT.
+ *               32-byte look-behind and, when one does, re-runs the document with PERSISTENT (same results).  UTF-8 of
+ *               sparse non-ASCII lanes is validated by a second kernel on an internal stream.  Whole documents only: the
+ *               chunked host path uses PERSISTENT.
  * A shape the chosen organisation does not support falls back to PERSISTENT / TILE for that call.
  */
 #define SJB200_KERNEL_AUTO 0
