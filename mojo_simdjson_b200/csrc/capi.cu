@@ -14,6 +14,10 @@
 #include "stage1_split.cuh"
 #include "stage1_stream.cuh"
 
+#ifndef SJ_K3_FW
+#define SJ_K3_FW 4   // warps (= chunks) per CTA of the flatten kernel (2 and 4: +0.8 % over 8, 16: -2 %)
+#endif
+
 using namespace sjb200;
 
 namespace {
@@ -188,7 +192,7 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     stage1_classify_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    constexpr int FW = 8;
+    constexpr int FW = SJ_K3_FW;
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
     return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, use_pdl(), p, c0, c1);
 }
@@ -221,7 +225,7 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
-    constexpr int FW = 8;
+    constexpr int FW = SJ_K3_FW;
     if (e == cudaSuccess)
         e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
     if (e == cudaSuccess && UTF8) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch
@@ -249,7 +253,7 @@ cudaError_t prepare_split(int *occ) {
         e = cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     cudaFuncSetAttribute(stage1_classify_kernel<NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_flatten_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     int a = 0, b = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_classify_kernel<NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);

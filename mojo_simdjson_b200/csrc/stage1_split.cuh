@@ -225,7 +225,7 @@ struct FlattenCfg {
 
 // chunks [chunk_begin, chunk_end): one warp each
 template <int FW>
-__global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
+__global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
     using Cfg = FlattenCfg<FW>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
