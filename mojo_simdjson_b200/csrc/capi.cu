@@ -423,6 +423,7 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
         c->launches += utf8 ? 5 : 4;
     }
     if (d.stream && whole && e != cudaSuccess) {
+        cudaMemsetAsync(c->ticket, 0, 256, stream);   // a half-issued pipeline may leave its chunk counter non-zero
         return cuda_err(e);
     } else if (d.split) {
         const int max_ctas = c->sm_count * c->split_occ[warps == 16 ? 1 : 0];
