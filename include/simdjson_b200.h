@@ -142,6 +142,17 @@ int32_t sjb200_copy_to_device(sjb200_ctx *ctx, void *d_dst, const void *h_src, u
 int32_t sjb200_copy_to_host(sjb200_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
 
 /*
+ * Side output for stage 2: d_bytes[k] = d_buf[d_idx[k]] for k < n, the byte every
+ * structural index points at.  The reference's stage 2 reads `buffer[next_structural[k]]` once per step
+ * (generic/stage2/json_iterator.mojo:256-262: a dependent random read); with this array the walk reads two sequential
+ * streams.  Asynchronous on the context's stream, after the stage-1 call that produced d_idx (n = its n_out; the trailer
+ * entries are not included).  An index >= len yields 0.  Any alignment of d_idx / d_bytes (16-byte-aligned d_idx with
+ * 4-byte-aligned d_bytes takes the vector path).
+ */
+int32_t sjb200_structural_bytes_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, const uint32_t *d_idx,
+                                             uint64_t n, uint8_t *d_bytes);
+
+/*
  * NDJSON / multi-document batches.  A batch is cut at '\n' into segments of at most seg_bytes (< 2^32) bytes;
  * every segment is an independent stage-1 call with segment-relative indexes, its own trailer and verdict --
  * exactly what the reference would produce if called once per segment.

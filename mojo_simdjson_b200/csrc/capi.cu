@@ -480,6 +480,33 @@ int32_t check_args(sjb200_ctx *c, uint64_t len, uint32_t flags) {
     return SJB200_SUCCESS;
 }
 
+// SURVEY.md section 8(f) rank 2 (first half): the byte every structural index points at.  Stage 2 reads
+// buffer[next_structural[k]] once per step (reference generic/stage2/json_iterator.mojo:256-262), a dependent random read
+// on the CPU; here it is one streaming pass: a thread takes four consecutive indexes (one 16-byte load), fetches the
+// four bytes (consecutive structurals are a few bytes apart, so a warp's 128 reads fall into a handful of lines) and
+// stores them as one 32-bit word.
+__global__ void __launch_bounds__(256) structural_bytes_kernel(const uint8_t *__restrict__ buf, uint32_t len, const uint32_t *__restrict__ idx,
+                                                             uint64_t n, uint8_t *__restrict__ out, uint32_t head) {
+    // [0, head): scalar until idx and out are 16- / 4-byte aligned together; then groups of four; then a scalar tail
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto byte_at = [&](uint32_t i) -> uint32_t { return i < len ? (uint32_t)__ldg(buf + i) : 0u; };
+    const uint64_t groups = (n - head) / 4;
+    if (t < groups) {
+        const uint64_t k = head + 4 * t;
+        const uint4 i4 = __ldcs(reinterpret_cast<const uint4 *>(idx + k));
+        const uint32_t w = byte_at(i4.x) | (byte_at(i4.y) << 8) | (byte_at(i4.z) << 16) | (byte_at(i4.w) << 24);
+        __stcs(reinterpret_cast<uint32_t *>(out + k), w);
+    } else {
+        // the ragged ends: at most `head` + 3 entries, one thread each
+        const uint64_t r = t - groups;
+        const uint64_t tail0 = head + 4 * groups;
+        uint64_t k = n;
+        if (r < head) k = r;
+        else if (r - head < n - tail0) k = tail0 + (r - head);
+        if (k < n) out[k] = (uint8_t)byte_at(idx[k]);
+    }
+}
+
 __global__ void split_kernel(const uint8_t *buf, uint64_t len, uint64_t seg_bytes, uint64_t *cuts, uint32_t ncuts) {
     // one warp per cut k: the position after the last '\n' inside (k*seg_bytes, min((k+1)*seg_bytes, len)],
     // or len itself for the final cut; ~0 if that window holds no newline.
@@ -808,6 +835,25 @@ int32_t sjb200_batch_split_host(const uint8_t *buf, uint64_t len, uint64_t seg_b
     }
     *n_segments = n;
     return SJB200_SUCCESS;
+}
+
+int32_t sjb200_structural_bytes_device_async(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, const uint32_t *d_idx, uint64_t n,
+                                             uint8_t *d_bytes) {
+    if (!c || (n && (!d_buf || !d_idx || !d_bytes))) return SJB200_UNINITIALIZED;
+    if (len > 0xFFFFFFFFull) return SJB200_CAPACITY;
+    if (n == 0) return SJB200_SUCCESS;
+    CK(cudaSetDevice(c->device));
+    // entries before the first position where idx is 16-byte aligned; the vector path also needs out + head 4-byte aligned
+    uint32_t head = (uint32_t)(((16 - (reinterpret_cast<uintptr_t>(d_idx) & 15)) & 15) / 4);
+    if (head > n) head = (uint32_t)n;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(d_bytes) + head) & 3) == 0;
+    if (!vec_ok) head = (uint32_t)(n < 0xFFFFFFFFull ? n : 0);   // misaligned pair of buffers: everything on the scalar path
+    if (!vec_ok && n >= 0xFFFFFFFFull) return SJB200_CAPACITY;
+    const uint64_t groups = (n - head) / 4;
+    const uint64_t threads = groups + head + ((n - head) - 4 * groups);
+    structural_bytes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_buf, (uint32_t)len, d_idx, n, d_bytes, head);
+    c->launches++;
+    return cuda_err(cudaGetLastError());
 }
 
 int32_t sjb200_batch_split_device(sjb200_ctx *c, const uint8_t *d_buf, uint64_t len, uint64_t seg_bytes,

@@ -86,6 +86,18 @@ class Stage1Context:
             return DeviceResult(rc, None, 0, 0)
         return self.finish()
 
+    def structural_bytes(self, buf: torch.Tensor, idx: torch.Tensor, n: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """out[k] = buf[idx[k]] for k < n (the byte each structural index points at), enqueued on the context's stream."""
+        assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
+        assert idx.is_cuda and idx.element_size() == 4 and idx.is_contiguous() and idx.numel() >= n
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=buf.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= n
+        rc = self._lib.sjb200_structural_bytes_device_async(self._ctx, buf.data_ptr(), buf.numel(), idx.data_ptr(), n, out.data_ptr())
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"structural byte gather failed: {errors.NAMES.get(rc, rc)}")
+        return out
+
     def last_elapsed_ms(self) -> float:
         return float(self._lib.sjb200_last_elapsed_ms(self._ctx))
 

@@ -112,3 +112,17 @@ def index_digest(idx: np.ndarray) -> tuple[int, int]:
     d0, d1 = C.c_uint64(0), C.c_uint64(0)
     L.oracle_index_digest(a.ctypes.data if a.size else None, int(a.size), C.byref(d0), C.byref(d1))
     return d0.value, d1.value
+
+
+def structural_bytes(data, indexes) -> np.ndarray:
+    """Side output for stage 2: the byte each structural index points at.
+
+    Restates what the reference's stage-2 walk reads at every step, `self.buf[self.next_structural[0]]` and its
+    `peek` variants (generic/stage2/json_iterator.mojo:256-262, :28-38): out[k] = data[indexes[k]]; an index at or
+    beyond len(data) -- the trailer entries are -- reads as 0 (the reference's buffer is zero padded there)."""
+    a = _as_u8(data)
+    idx = np.asarray(indexes, dtype=np.uint32).astype(np.int64)
+    out = np.zeros(idx.size, dtype=np.uint8)
+    ok = idx < a.size
+    out[ok] = a[idx[ok]]
+    return out

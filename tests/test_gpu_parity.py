@@ -569,3 +569,36 @@ def test_utf8_verdicts_sparse_lanes(dev, scratch, kernel):
     res, out = run_device(dev, scratch, data, flags=1, kernel=kernel, warps=8)
     assert_same(res, out, want)
     assert want.utf8_error == 1
+
+
+def test_structural_bytes_side_output(dev, scratch):
+    """out[k] = buf[idx[k]] on the device against the oracle, every alignment of idx / out."""
+    from mojo_simdjson_b200 import synth
+
+    docs = [b"[1]", b'{"a":[1,-2.5e3,true,null,"x\\"y"],"b":{}}', bytes(synth.twitter_like()), bytes(synth.status_array(3 << 20))]
+    for data in docs:
+        want = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+        assert want.error == 0
+        wb = oracle.structural_bytes(data, want.indexes[: want.n])
+        inp = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+        idx_buf = torch.full((len(data) + 16,), -1, dtype=torch.int32, device="cuda")
+        out_buf = torch.full((len(data) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+        for ishift in (0, 1, 2, 3):
+            for oshift in (0, 1, 3, 4):
+                idx = idx_buf[ishift:]
+                res = dev.index(inp, idx)
+                assert res.error == 0 and res.n == want.n
+                out_buf.fill_(0xEE)
+                out = out_buf[8 + oshift :]
+                dev.structural_bytes(inp, idx, res.n, out)
+                torch.cuda.synchronize()
+                got = out[: res.n].cpu().numpy()
+                assert np.array_equal(got, wb), (len(data), ishift, oshift)
+                assert int(out_buf[7 + oshift]) == 0xEE and int(out[res.n]) == 0xEE, "wrote outside [0, n)"
+    # the trailer entries (len, len, 0) read as 0, 0 and the first byte
+    data = docs[1]
+    inp = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    idx = torch.empty(len(data) + 3, dtype=torch.int32, device="cuda")
+    res = dev.index(inp, idx)
+    got = dev.structural_bytes(inp, idx, res.n + 3).cpu().numpy()
+    assert list(got[-3:]) == [0, 0, data[0]]

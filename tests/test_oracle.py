@@ -173,3 +173,12 @@ def test_digest_is_order_sensitive():
     b[[2, 3]] = b[[3, 2]]
     assert oracle.index_digest(a) != oracle.index_digest(b)
     assert oracle.index_digest(a) == oracle.index_digest(a.copy())
+
+
+def test_structural_bytes_side_output():
+    """Every structural index of a valid document points at an operator, a quote or the first byte of a scalar."""
+    data = b'{"a":[1,-2.5e3,true,null,"x\\"y"],"b":{}}'
+    r = oracle.stage1(data)
+    got = oracle.structural_bytes(data, r.indexes[: r.n])
+    assert bytes(got) == b'{":[1,-,t,n,"],":{}}'
+    assert list(oracle.structural_bytes(data, r.indexes[: r.n + 3])[-3:]) == [0, 0, ord("{")]  # len, len, 0
