@@ -408,8 +408,13 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
         }
     }
     // escapes and quotes, exact; structural bits for both in-string parities
-    const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
-    const uint32_t bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
+    // A = lanes that are one long backslash run, O = parity of the backslash run each lane ends with; both are zero unless
+    // some lane ends in a backslash, which one ballot on the top bit decides
+    uint32_t bA = 0, bO = 0;
+    if (__ballot_sync(0xFFFFFFFFu, (uint32_t)(m.bs >> 32) >> 31)) {
+        bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
+        bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
+    }
     const LaneQuotes q = lane_quotes(m, warp_lane_e_in(bA, bO, lane, in.wst.e));
     const uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (q.ps >> 63) != 0);
     const uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (q.nqs >> 63) != 0);
