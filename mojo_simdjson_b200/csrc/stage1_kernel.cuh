@@ -56,9 +56,6 @@
 #ifndef SJ_TRACE
 #define SJ_TRACE 0
 #endif
-#ifndef SJ_LEAN_FLATTEN
-#define SJ_LEAN_FLATTEN 0
-#endif
 
 namespace sjb200 {
 
@@ -499,57 +496,8 @@ __device__ __forceinline__ void write_verdict(const Stage1Params &P, const TileP
     }
 }
 
-// flatten one lane's structural bits (BitIndexer.write, :46-58) into dst[0..].  The words are bit-reversed so that one
-// FLO finds the lowest structural; per index: FLO (XU) + subtract (value) + shift + and-with-predicate + store.
-__device__ __forceinline__ void flatten_word(uint32_t *&dst, uint32_t bits, uint32_t v31) {
-#if SJ_LEAN_FLATTEN == 2
-    // four indexes per trip: the clear-lowest-bit chain is cheap (IADD + LOP3), the four position searches (one FLO on
-    // the isolated bit each) are independent and overlap -- a warp issues in order, so one FLO per trip of a rolled
-    // loop would expose the full XU latency every iteration
-    const uint32_t v0 = v31 - 31u;
-    while (bits) {
-        const uint32_t t1 = bits & (bits - 1u), t2 = t1 & (t1 - 1u), t3 = t2 & (t2 - 1u);
-        const uint32_t p0 = 31u - (uint32_t)__clz((int)(bits & (0u - bits)));
-        const uint32_t p1 = 31u - (uint32_t)__clz((int)(t1 & (0u - t1)));
-        const uint32_t p2 = 31u - (uint32_t)__clz((int)(t2 & (0u - t2)));
-        const uint32_t p3 = 31u - (uint32_t)__clz((int)(t3 & (0u - t3)));
-        dst[0] = v0 + p0;
-        if (t1) dst[1] = v0 + p1;
-        if (t2) dst[2] = v0 + p2;
-        if (t3) dst[3] = v0 + p3;
-        dst += 1 + (t1 != 0) + (t2 != 0) + (t3 != 0);
-        bits = t3 & (t3 - 1u);
-    }
-#elif SJ_LEAN_FLATTEN == 3
-    // position of the lowest set bit = popc(bits ^ (bits - 1)) - 1: one XU op per index, no bit reversal, and the
-    // bits - 1 it needs is the same one that clears the bit
-    const uint32_t vm1 = v31 - 32u;
-    while (bits) {
-        const uint32_t t = bits - 1u;
-        *dst++ = vm1 + (uint32_t)__popc(bits ^ t);
-        bits &= t;
-    }
-#elif SJ_LEAN_FLATTEN
-    uint32_t r = __brev(bits);
-    while (r) {
-        const uint32_t h = 31u - (uint32_t)__clz((int)r);  // FLO: highest set bit of the reversed word
-        *dst++ = v31 - h;                                    // = v0 + (position of the lowest set bit)
-        r &= ~(1u << h);
-    }
-#else
-    // The word is bit-reversed once; bfind (FLO in SASS) then returns 31 - (position of the lowest structural) directly.
-    // Per index: FLO, subtract, shift, xor (also sets the loop predicate), store, pointer bump, branch.  bfind is
-    // inline PTX on purpose: written with __clz / __ffs the compiler re-derives the position as 31 - FLO and clears
-    // the bit with a shifted 0x80000000 and a separate NOT, three instructions more per index.
-    uint32_t r = __brev(bits);
-    while (r) {
-        uint32_t h;
-        asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(r));
-        *dst++ = v31 - h;
-        r ^= 1u << h;   // bit h is set: xor clears it (and-not costs a separate NOT here)
-    }
-#endif
-}
+// flatten one lane's structural bits (BitIndexer.write, reference json_structural_indexer.mojo:46-58) into a staging area in
+// shared memory.
 // Flattening is bound by instruction issue, so its two inner pieces are written out by hand.
 //
 // flatten_word_pair: the structurals of one 32-bit word into shared memory at byte address `sptr`, two per trip.  The
@@ -615,28 +563,9 @@ __device__ __forceinline__ void copy_out_warp(const uint32_t *stage, uint32_t a,
 }
 
 __device__ __forceinline__ void flatten_to(uint32_t *dst, uint64_t structural, uint32_t v0) {
-#if SJ_LEAN_FLATTEN == 4
-    // both 32-bit words at once: two independent clear-lowest-bit chains per trip, half the trips (a warp issues in
-    // order, so the loop is bound by the latency of one trip, not by its instruction count)
-    uint32_t lo = (uint32_t)structural, hi = (uint32_t)(structural >> 32);
-    uint32_t *dhi = dst + __popc(lo);
-    const uint32_t vl = v0 - 1u, vh = v0 + 31u;
-    while (lo | hi) {
-        const uint32_t tl = lo - 1u, th = hi - 1u;
-        const uint32_t pl = (uint32_t)__popc(lo ^ tl), ph = (uint32_t)__popc(hi ^ th);
-        if (lo) *dst++ = vl + pl;
-        if (hi) *dhi++ = vh + ph;
-        lo = lo ? (lo & tl) : 0u;
-        hi = hi ? (hi & th) : 0u;
-    }
-#elif SJ_LEAN_FLATTEN
-    flatten_word(dst, (uint32_t)structural, v0 + 31u);
-    flatten_word(dst, (uint32_t)(structural >> 32), v0 + 63u);
-#else
     const uint32_t lo = (uint32_t)structural, sp = smem_u32(dst);   // dst is always a shared-memory staging area
     flatten_word_pair(sp, lo, v0 + 31u);
     flatten_word_pair(sp + 4u * (uint32_t)__popc(lo), (uint32_t)(structural >> 32), v0 + 63u);
-#endif
 }
 __device__ __forceinline__ void flatten_direct(uint32_t *out, uint64_t cap, uint64_t o, uint64_t structural, uint32_t v0) {
     uint32_t rlo = __brev((uint32_t)structural), rhi = __brev((uint32_t)(structural >> 32));
