@@ -29,12 +29,6 @@
 #ifndef SJ_NSLEEP
 #define SJ_NSLEEP 20
 #endif
-#ifndef SJ_DEPTH
-#define SJ_DEPTH 1
-#endif
-#ifndef SJ_PRODUCE_LATE
-#define SJ_PRODUCE_LATE 0
-#endif
 #ifndef SJ_FLOWREG8
 #define SJ_FLOWREG8 56
 #endif

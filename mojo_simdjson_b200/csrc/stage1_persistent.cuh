@@ -53,7 +53,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *smem_in = smem_raw;                                           // [0,16) halo, [16, 16+TILE) tile
     uint32_t *smem_stage = reinterpret_cast<uint32_t *>(smem_raw + ((Cfg::IN_BYTES + 127) & ~127));
-    constexpr int NS = 4;                        // hand-off slots (a tile is flushed two tiles after its phase 1)
+    constexpr int NS = 4;                        // hand-off slots (a tile is flushed one iteration after its phase 1)
     __shared__ __align__(8) uint64_t s_bar[2 + 2 * NS];  // 0 in_full, 1 in_empty, 2.. sum_full[NS], 2+NS.. carry_full[NS]
     __shared__ TileSlot s_slot[NS];
     __shared__ int32_t s_tile_of;               // tile held by the input buffer, -1 = no more work
@@ -155,13 +155,13 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
     } else {
         // =============================== compute warps ===============================
         uint32_t *stage = smem_stage + warp * (Cfg::WCAP + 4);
-        // the two previous tiles of this warp, waiting for their look-backs (registers)
+        // the previous tile of this warp, waiting for its look-back (registers).  Holding two tiles was measured: worse.
         struct Held {
             uint64_t m0, m1;
             uint32_t c0, c1, v0;
         };
-        Held old1 = {0, 0, 0, 0, 0}, old2 = {0, 0, 0, 0, 0};  // tile i-1, tile i-2
-        int n_held = 0;
+        Held old1 = {0, 0, 0, 0, 0};
+        bool held = false;
         int i = 0;
 
         // flatten a held tile (iteration `it`) once its look-back has delivered parity and cursor
@@ -216,7 +216,6 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
             {
                 LaneInput in;
                 warp_load<UTF8>(in, smem_in + 16, warp, lane, tile, tb, TILE, P);
-#if !SJ_PRODUCE_LATE
                 __syncwarp();
                 if (lane == 0) {                            // this warp no longer needs the input buffer
                     __threadfence_block();
@@ -226,7 +225,6 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
                         produce(i + 1);
                     }
                 }
-#endif
 #if SJ_SKIP_COMPUTE
                 // debug: pretend every 6th byte is structural, no classification at all
                 ph.m0 = 0x0410410410410410ull ^ in.w[0]; ph.m1 = ~ph.m0; ph.c0 = (uint32_t)__popcll(ph.m0); ph.c1 = 64 - ph.c0;
@@ -266,33 +264,21 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
                     S.agg = packed;
                     S.tile = tile;
                     S.arrived = 0;
-#if SJ_PRODUCE_LATE
-                    produce(i + 1);  // ticket order == aggregate publication order: successors never wait long for us
-#endif
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sum + 8 * slot);     // release: slot contents visible to the scan warp
             }
-            // flatten tile i-2: its look-back has had two phase-1 times to complete
-#if SJ_DEPTH == 1
-            if (n_held >= 1) {
-                flush_old(old1, i - 1);
-                n_held = 0;
-            }
-#else
-            if (n_held == 2) flush_old(old2, i - 2);
-#endif
-            old2 = old1;
+            // flatten tile i-1: its look-back ran on the scan warp during phase 1 of tile i
+            if (held) flush_old(old1, i - 1);
             old1.m0 = ph.m0;
             old1.m1 = ph.m1;
             old1.c0 = ph.c0;
             old1.c1 = ph.c1;
             old1.v0 = ph.v0;
-            if (n_held < 2) n_held++;
+            held = true;
             i++;
         }
-        if (n_held == 2) flush_old(old2, i - 2);
-        if (n_held >= 1) flush_old(old1, i - 1);
+        if (held) flush_old(old1, i - 1);
     }
 }
 
