@@ -330,9 +330,9 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
         in.w[4 * q + 3] = v.w;
     }
     in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(smem_tile + off - 4) : 0u;
-    in.ends = 0;
+    // the document may end exactly with this lane's last byte (also when the last tile is full: not an "edge" tile then)
+    in.ends = (tile == (int)P.ntiles - 1) && (in.g0 + 64 == alen);
     if (edge) {  // only the first and last tile: bytes outside [mis, alen) read as 0x20 (reference tail padding)
-        in.ends = in.g0 + 64 == alen;
 #pragma unroll
         for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
         if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);

@@ -46,8 +46,8 @@ struct StreamCfg {
 // phase 1 input of one lane from the warp's private buffer; `chunk` points at the chunk's first byte, HALO bytes before it
 // are the preceding input (chunk > 0).  `edge`: first chunk, or a last chunk that is not full.
 template <bool UTF8>
-__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, bool edge, const Stage1Params &P,
-                                           uint32_t &unresolved) {
+__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, bool edge, bool is_last,
+                                           uint32_t last_bytes, const Stage1Params &P, uint32_t &unresolved) {
     in.g0 = (int64_t)c * 2048 + lane * 64;
     const uint4 *src = reinterpret_cast<const uint4 *>(chunk + lane * 64);
 #pragma unroll
@@ -59,10 +59,10 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
         in.w[4 * q + 3] = v.w;
     }
     in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(chunk + lane * 64 - 4) : 0u;
-    in.ends = 0;
+    // the document may end exactly with this lane's last byte (also when the last chunk is full: not an "edge" chunk then)
+    in.ends = is_last && ((uint32_t)lane * 64u + 64u == last_bytes);
     if (edge) {  // bytes outside [mis, alen) read as 0x20 (reference tail padding)
         const int64_t alen = (int64_t)P.alen;
-        in.ends = in.g0 + 64 == alen;
 #pragma unroll
         for (int k = 0; k < 16; k++) in.w[k] = mask_word(in.w[k], in.g0 + 4 * k, (int64_t)P.mis, alen);
         if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             LaneInput in;
             uint32_t unresolved;
             const bool edge = (c == 0u) || (c == last && last_partial);
-            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, P, unresolved);
+            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, unresolved);
             __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
             if (lane == 0) {
                 fetch(b);

@@ -89,6 +89,8 @@ def stage1(data, flags: int = 0, impl: str = "ref", cap: int | None = None, nati
     if impl == "fast":
         err = L.oracle_stage1_fast(ptr, n_bytes, out.ctypes.data, cap, C.byref(n), C.byref(nw), flags)
         u8.value = 0 if L.oracle_utf8_valid_dfa(ptr, n_bytes) else 1
+        if (flags & 1) and err == SUCCESS and u8.value:
+            err = UTF8_ERROR  # same priority slot as oracle_stage1_ref: only a would-be SUCCESS turns into UTF8_ERROR
     else:
         f = L.oracle_stage1_ref if impl == "ref" else L.oracle_stage1_spec
         err = f(ptr, n_bytes, out.ctypes.data, cap, C.byref(n), C.byref(nw), C.byref(u8), flags)

@@ -97,6 +97,15 @@ def adversarial_cases(tile_bytes=(4096, 8192, 16384), heavy: bool = False):
         add(f"len:{n}:digits", (b"[" + b"1," * n)[:n])
         add(f"len:{n}:string", (b'"' + b"a" * n)[: n - 1] + b'"' if n >= 2 else b"1")
 
+    # truncated / complete multi-byte sequences at the very end of documents whose length is an exact multiple of every
+    # chunk and tile size (the last lane of a FULL last chunk owns the end-of-input check), also one byte either side
+    for total in sorted({2048, 4096, 6144} | set(tile_bytes) | {2 * t for t in tile_bytes}):
+        for tail in (b"\xc3", b"\xe2\x82", b"\xf0\x9f\x98", "é".encode(), "€".encode(), "😀".encode()):
+            for d in (-1, 0, 1):
+                n = total + d
+                add(f"utf8-end:{n}:{tail.hex()}", b'"' + b"a" * (n - 1 - len(tail)) + tail)
+                add(f"utf8-end-closed:{n}:{tail.hex()}", b'"' + b"a" * (n - 2 - len(tail)) + tail + b'"')
+
     # (i) backslash runs of every length at several offsets, inside a string, then a quote
     long_runs = [4095, 4096, 4097] + ([65535, 65536, (1 << 20) + 1] if heavy else [])
     for run in list(range(1, 131)) + long_runs:

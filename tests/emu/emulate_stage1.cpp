@@ -376,9 +376,8 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
             uint32_t words[16], prev;
             memcpy(words, chunk + l * 64, 64);
             memcpy(&prev, chunk + l * 64 - 4, 4);
-            bool ends = false;
+            const bool ends = (c == last) && ((int64_t)l * 64 + 64 == last_bytes);  // also when the last chunk is full
             if (edge) {
-                ends = g0 + 64 == alen;
                 for (int k = 0; k < 16; k++) words[k] = mask_word(words[k], g0 + 4 * k, mis, alen);
                 prev = (g0 == 0) ? 0x20202020u : mask_word(prev, g0 - 4, mis, alen);
             }
