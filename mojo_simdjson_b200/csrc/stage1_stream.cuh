@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) stage1_utf8_lanes_kernel(const Stage1Para
 }
 
 // ---------------------------------------------------------------------------------------------
-// ordered scan of chunk summaries (1024 per CTA, one per thread)
+// ordered scan of chunk summaries (SPAN_BLOCK = 4096 per CTA, four consecutive ones per thread)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ SpanAcc span_from_summary(const uint4 s) {
     SpanAcc a;
