@@ -153,6 +153,19 @@ int32_t sjb200_structural_bytes_device_async(sjb200_ctx *ctx, const uint8_t *d_b
                                              uint64_t n, uint8_t *d_bytes);
 
 /*
+ * Second side output for stage 2: where top-level documents start in a stream of
+ * structurals -- NDJSON or any concatenation of documents indexed by ONE stage-1 call (the reference has no document
+ * stream mode: generic/stage2/tape_builder.mojo:25 "TODO: add streaming").  With depth(k) = #('{' '[') - #('}' ']') among
+ * the structural bytes [0, k), d_starts[k] = 1 if depth(k) == 0, else 0: structural k opens a document (a top-level
+ * scalar is a document of one structural).  d_bytes is the output of sjb200_structural_bytes_device_async (n entries).
+ * d_scratch: int32[scratch_entries], at least ceil(n / 4096) entries (CAPACITY otherwise); on return it holds the depth
+ * before every block of 4096 structurals.  Unbalanced input is not an error here (depths may go negative; stage 2
+ * diagnoses that).  Asynchronous on the context's stream.
+ */
+int32_t sjb200_document_starts_device_async(sjb200_ctx *ctx, const uint8_t *d_bytes, uint64_t n, uint8_t *d_starts,
+                                            int32_t *d_scratch, uint64_t scratch_entries);
+
+/*
  * NDJSON / multi-document batches.  A batch is cut at '\n' into segments of at most seg_bytes (< 2^32) bytes;
  * every segment is an independent stage-1 call with segment-relative indexes, its own trailer and verdict --
  * exactly what the reference would produce if called once per segment.

@@ -507,6 +507,116 @@ __global__ void __launch_bounds__(256) structural_bytes_kernel(const uint8_t *__
     }
 }
 
+// SURVEY.md section 8(f) rank 2 (second half): where top-level documents start in a stream of structurals (NDJSON, or
+// any concatenation of documents).  depth(k) = number of '{' '[' minus number of '}' ']' among structurals [0, k); a
+// structural with depth(k) == 0 is the first one of a document.  Three launches: per 4096 structurals the sum of the
+// +1 / -1 steps; an exclusive scan of those sums by one CTA; then every thread re-walks its 16 structurals from the
+// block's depth.  All of it on bytes produced by structural_bytes_kernel.
+constexpr int DEPTH_PER_THREAD = 16, DEPTH_THREADS = 256, DEPTH_BLOCK = DEPTH_PER_THREAD * DEPTH_THREADS;
+
+__device__ __forceinline__ int depth_step(uint32_t b) {      // '{' 7B '[' 5B -> +1, '}' 7D ']' 5D -> -1
+    const uint32_t low = b | 0x20u;                            // fold [ ] onto { }
+    return low == 0x7Bu ? 1 : (low == 0x7Du ? -1 : 0);
+}
+// loads thread t's 16 bytes of the block (zero beyond n: zero is not a bracket)
+__device__ __forceinline__ void depth_load(const uint8_t *bytes, uint64_t n, uint64_t k0, uint32_t w[4]) {
+    if ((reinterpret_cast<uintptr_t>(bytes + k0) & 15) == 0 && k0 + 16 <= n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bytes + k0));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t k = k0 + 4 * q + j;
+                if (k < n) x |= (uint32_t)__ldg(bytes + k) << (8 * j);
+            }
+            w[q] = x;
+        }
+    }
+}
+__device__ __forceinline__ int block_sum_i32(int v, int *s_w) {   // sum over the CTA's 256 threads, result in every thread
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int q = 0; q < DEPTH_THREADS / 32; q++) t += s_w[q];
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(DEPTH_THREADS) depth_block_sums_kernel(const uint8_t *__restrict__ bytes, uint64_t n, int *__restrict__ block_sum) {
+    __shared__ int s_w[DEPTH_THREADS / 32];
+    const uint64_t k0 = (uint64_t)blockIdx.x * DEPTH_BLOCK + (uint64_t)threadIdx.x * DEPTH_PER_THREAD;
+    uint32_t w[4];
+    depth_load(bytes, n, k0, w);
+    int d = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) d += depth_step((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    const int total = block_sum_i32(d, s_w);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
+}
+// one CTA: block_sum[b] <- depth before block b (exclusive scan, in place)
+__global__ void __launch_bounds__(1024) depth_scan_blocks_kernel(int *block_sum, uint32_t nblocks) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024u) {
+        const uint32_t b = b0 + threadIdx.x;
+        const int v = b < nblocks ? block_sum[b] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)(threadIdx.x & 31) >= d) incl += o;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int before_warp = 0;
+        for (int q = 0; q < (int)(threadIdx.x >> 5); q++) before_warp += s_w[q];
+        const int carry = s_carry;
+        if (b < nblocks) block_sum[b] = carry + before_warp + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + before_warp + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(DEPTH_THREADS) depth_starts_kernel(const uint8_t *__restrict__ bytes, uint64_t n, const int *__restrict__ block_depth,
+                                                                   uint8_t *__restrict__ starts) {
+    __shared__ int s_w[DEPTH_THREADS / 32];
+    const uint64_t k0 = (uint64_t)blockIdx.x * DEPTH_BLOCK + (uint64_t)threadIdx.x * DEPTH_PER_THREAD;
+    uint32_t w[4];
+    depth_load(bytes, n, k0, w);
+    int d = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) d += depth_step((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    // exclusive prefix of the per-thread sums inside the CTA
+    int incl = d;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+        if ((int)(threadIdx.x & 31) >= s) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int depth = block_depth[blockIdx.x] + incl - d;
+    for (int q = 0; q < (int)(threadIdx.x >> 5); q++) depth += s_w[q];
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (depth == 0) o[j >> 2] |= 1u << (8 * (j & 3));
+        depth += depth_step((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    }
+    if ((reinterpret_cast<uintptr_t>(starts + k0) & 15) == 0 && k0 + 16 <= n) {
+        *reinterpret_cast<uint4 *>(starts + k0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int j = 0; j < 16; j++)
+            if (k0 + j < n) starts[k0 + j] = (uint8_t)((o[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    }
+}
+
 __global__ void split_kernel(const uint8_t *buf, uint64_t len, uint64_t seg_bytes, uint64_t *cuts, uint32_t ncuts) {
     // one warp per cut k: the position after the last '\n' inside (k*seg_bytes, min((k+1)*seg_bytes, len)],
     // or len itself for the final cut; ~0 if that window holds no newline.
@@ -853,6 +963,20 @@ int32_t sjb200_structural_bytes_device_async(sjb200_ctx *c, const uint8_t *d_buf
     const uint64_t threads = groups + head + ((n - head) - 4 * groups);
     structural_bytes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_buf, (uint32_t)len, d_idx, n, d_bytes, head);
     c->launches++;
+    return cuda_err(cudaGetLastError());
+}
+
+int32_t sjb200_document_starts_device_async(sjb200_ctx *c, const uint8_t *d_bytes, uint64_t n, uint8_t *d_starts, int32_t *d_scratch,
+                                            uint64_t scratch_entries) {
+    if (!c || (n && (!d_bytes || !d_starts || !d_scratch))) return SJB200_UNINITIALIZED;
+    if (n == 0) return SJB200_SUCCESS;
+    const uint64_t nblocks = (n + DEPTH_BLOCK - 1) / DEPTH_BLOCK;
+    if (nblocks > scratch_entries || nblocks > 0x7FFFFFFFull) return SJB200_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    depth_block_sums_kernel<<<(unsigned)nblocks, DEPTH_THREADS, 0, c->stream>>>(d_bytes, n, d_scratch);
+    depth_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(d_scratch, (uint32_t)nblocks);
+    depth_starts_kernel<<<(unsigned)nblocks, DEPTH_THREADS, 0, c->stream>>>(d_bytes, n, d_scratch, d_starts);
+    c->launches += 3;
     return cuda_err(cudaGetLastError());
 }
 

@@ -98,6 +98,19 @@ class Stage1Context:
             raise RuntimeError(f"structural byte gather failed: {errors.NAMES.get(rc, rc)}")
         return out
 
+    def document_starts(self, structural_bytes: torch.Tensor, n: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """out[k] = 1 iff structural k opens a top-level document (bracket depth before it is 0); see the C header."""
+        assert structural_bytes.is_cuda and structural_bytes.dtype == torch.uint8 and structural_bytes.numel() >= n
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=structural_bytes.device)
+        scratch = torch.empty(max(1, -(-n // 4096)), dtype=torch.int32, device=structural_bytes.device)
+        rc = self._lib.sjb200_document_starts_device_async(self._ctx, structural_bytes.data_ptr(), n, out.data_ptr(),
+                                                           scratch.data_ptr(), scratch.numel())
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"document start scan failed: {errors.NAMES.get(rc, rc)}")
+        self._depth_scratch = scratch  # keep it alive until the stream has used it
+        return out
+
     def last_elapsed_ms(self) -> float:
         return float(self._lib.sjb200_last_elapsed_ms(self._ctx))
 

@@ -128,3 +128,17 @@ def structural_bytes(data, indexes) -> np.ndarray:
     ok = idx < a.size
     out[ok] = a[idx[ok]]
     return out
+
+
+def document_starts(structural_byte_values) -> np.ndarray:
+    """Side output for stage 2: out[k] = 1 iff structural k opens a top-level document,
+    i.e. the bracket depth over the structural bytes before it is 0.  The reference has no document-stream mode
+    (generic/stage2/tape_builder.mojo:25 "TODO: add streaming"); the depth bookkeeping restated here is the one its
+    stage-2 walk does one container at a time (generic/stage2/json_iterator.mojo:40-254: depth += 1 at '{' / '[',
+    depth -= 1 at '}' / ']', a document is finished when depth returns to 0)."""
+    b = np.asarray(structural_byte_values, dtype=np.uint8)
+    step = np.zeros(b.size, dtype=np.int64)
+    step[(b == ord("{")) | (b == ord("["))] = 1
+    step[(b == ord("}")) | (b == ord("]"))] = -1
+    before = np.cumsum(step) - step
+    return (before == 0).astype(np.uint8)

@@ -602,3 +602,35 @@ def test_structural_bytes_side_output(dev, scratch):
     res = dev.index(inp, idx)
     got = dev.structural_bytes(inp, idx, res.n + 3).cpu().numpy()
     assert list(got[-3:]) == [0, 0, data[0]]
+
+
+def test_document_starts_side_output(dev):
+    """SURVEY 8(f) rank 2, second half: depth-0 structurals of a document stream, against the oracle's cumulative sum."""
+    from mojo_simdjson_b200 import synth
+
+    docs = [b"1", b'{"a":[1,2]}\n[3]\n4 "s"\n{"b":{}}', b"]]][[[", bytes(synth.ndjson(24 << 20)), bytes(synth.status_array(5 << 20))]
+    for data in docs:
+        want = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+        n = want.n_written
+        sb = oracle.structural_bytes(data, want.indexes[:n])
+        ws = oracle.document_starts(sb)
+        for shift in (0, 1, 5, 16):
+            buf = torch.full((n + 64,), 0x7B, dtype=torch.uint8, device="cuda")   # hostile bytes around: '{'
+            view = buf[shift : shift + n]
+            view.copy_(torch.from_numpy(sb))
+            out_buf = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+            out = out_buf[8 + shift :]
+            dev.document_starts(view, n, out)
+            torch.cuda.synchronize()
+            assert np.array_equal(out[:n].cpu().numpy(), ws), (len(data), shift)
+            assert int(out_buf[7 + shift]) == 0xEE and int(out[n]) == 0xEE, "wrote outside [0, n)"
+    # the whole chain on the device: index -> bytes -> starts; an NDJSON batch has one start per line
+    data = docs[3]
+    inp = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    idx = torch.empty(len(data) // 2, dtype=torch.int32, device="cuda")
+    res = dev.index(inp, idx)
+    assert res.error == 0
+    sbytes = dev.structural_bytes(inp, idx, res.n)
+    starts = dev.document_starts(sbytes, res.n)
+    torch.cuda.synchronize()
+    assert int(starts.sum().item()) == data.count(b"\n")

@@ -182,3 +182,12 @@ def test_structural_bytes_side_output():
     got = oracle.structural_bytes(data, r.indexes[: r.n])
     assert bytes(got) == b'{":[1,-,t,n,"],":{}}'
     assert list(oracle.structural_bytes(data, r.indexes[: r.n + 3])[-3:]) == [0, 0, ord("{")]  # len, len, 0
+
+
+def test_document_starts_side_output():
+    data = b'{"a":[1,2]}\n[3]\n4 "s"\n{"b":{}}'
+    r = oracle.stage1(data)
+    sb = oracle.structural_bytes(data, r.indexes[: r.n])
+    assert bytes(sb) == b'{":[1,2]}[3]4"{":{}}'
+    starts = oracle.document_starts(sb)
+    assert [k for k, f in enumerate(starts) if f] == [0, 9, 12, 13, 14]   # { [ 4 " {

@@ -1,4 +1,4 @@
-"""Timing of the stage-2 side output (structural bytes) on the 1 GiB document.  usage: python tools/side_outputs.py [mib]"""
+"""Timing of the stage-2 side outputs (structural bytes, document starts) on the 1 GiB document.  usage: python tools/side_outputs.py [mib]"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mojo_simdjson_b200 import device, synth
@@ -18,3 +18,12 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 moved = size + 5 * res.n
 print('structural bytes: n', res.n, 'ms %.4f' % ms, 'input GB/s %.0f' % (size / ms / 1e6), 'algorithmic GB/s (input + 4n + n) %.0f' % (moved / ms / 1e6))
+
+d_s = torch.empty(res.n, dtype=torch.uint8, device='cuda')
+for _ in range(3): ctx.document_starts(d_b, res.n, d_s)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20): ctx.document_starts(d_b, res.n, d_s)
+e1.record(); torch.cuda.synchronize()
+ms2 = e0.elapsed_time(e1) / 20
+print('document starts: ms %.4f' % ms2, 'GB/s over n bytes in + n bytes out (+ n read again) %.0f' % (3 * res.n / ms2 / 1e6), 'starts', int(d_s.sum().item()))
