@@ -371,6 +371,13 @@ def run_ours(args):
     kev1.record(stream)
     torch.cuda.synchronize()
     k_ms = kev0.elapsed_time(kev1) / kreps / nseg  # per document pass
+    if n_gpus == 1:
+        # at N = 1 a timed step IS one document pass (same launches, same stream, same events): report the roofline from
+        # the timed region itself so that `value` and `roofline.achieved` can never disagree; the loop above is kept as a
+        # cross-check
+        k_ms_check, k_ms = k_ms, ms_step
+    else:
+        k_ms_check = k_ms
     alg_bytes = (size + 4 * (n_total + 3 * nseg)) / nseg  # per pass: input read once + every index written once
     peak, peak_kind = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -387,7 +394,7 @@ def run_ours(args):
                  "split": "stage1_classify_kernel + stage1_flatten_kernel"}[kind]
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": prof.get("dram_bytes_per_pass"), "peak_source": f"of {peak_kind}",
-                "kernel": kname, "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
+                "kernel": kname, "kernel_ms": round(k_ms, 4), "kernel_ms_second_loop": round(k_ms_check, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
                 "structural_density": round(density, 4),
                 "note": "achieved = algorithmic bytes of one document pass / device time of ALL its launches (CUDA events)",
                 "ncu_kernel_shares": prof.get("kernel_shares")}
