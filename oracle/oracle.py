@@ -7,6 +7,7 @@ cpu_baseline / --impl reference legs import this module.  The product path
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import subprocess
 from dataclasses import dataclass
@@ -19,12 +20,36 @@ SUCCESS, CAPACITY, UTF8_ERROR, EMPTY, UNESCAPED_CHARS, UNCLOSED_STRING, UNEXPECT
 FLAG_VALIDATE_UTF8 = 1
 
 
+def _cpu_signature() -> str:
+    """The host's CPU feature flags: a -march=native build must not be carried to a machine with different ones."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(native: bool = False) -> str:
     target = "liboracle_stage1_native.so" if native else "liboracle_stage1.so"
     path = os.path.join(_HERE, target)
     src = os.path.join(_HERE, "stage1_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    stale = not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src)
+    sig_path = path + ".cpu"
+    if native and not stale:   # built on another machine (it travels with the repository snapshot)?
+        try:
+            stale = open(sig_path).read().strip() != _cpu_signature()
+        except OSError:
+            stale = True
+    if stale:
+        if os.path.exists(path):
+            os.remove(path)
         subprocess.check_call(["make", "-s", "-C", _HERE, target])
+        if native:
+            with open(sig_path, "w") as f:
+                f.write(_cpu_signature())
     return path
 
 
