@@ -125,7 +125,7 @@ def parse_args():
     ap.add_argument("--bytes-per-gpu", type=int, default=GIB)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--warps", type=int, default=0, help="force tile shape (2/4/8), 0 = auto")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "tile", "persistent", "dataflow", "split", "stream"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "split", "stream", "fused"],
                     help="force the kernel organisation (sjb200_ctx_set_kernel); auto = the library's choice")
     ap.add_argument("--no-utf8", action="store_true", help="skip UTF-8 validation (the reference validates nothing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -383,15 +383,16 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # which kernel organisation the library picks for this document size (capi.cu: SPLIT_MIN_BYTES) unless forced
     seg = size / nseg
-    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (160 << 20) else ("split" if seg >= (48 << 20) else "persistent"))
+    kind = args.kernel if args.kernel != "auto" else ("fused" if seg >= (8 << 20) else "persistent")
     prof = ncu_traffic(kind)
     if kind == "stream":
         kname = ("stage-1 stream pipeline, 6 launches per document: stage1_stream_classify_kernel -> stage1_utf8_lanes_kernel -> "
                  "stage1_span_reduce_kernel -> stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a "
                  "no-op fallback)")
     else:
-        kname = {"persistent": "stage1_persistent_kernel", "dataflow": "stage1_dataflow_kernel", "tile": "stage1_kernel",
-                 "split": "stage1_classify_kernel + stage1_flatten_kernel"}[kind]
+        kname = {"persistent": "stage1_persistent_kernel", "split": "stage1_classify_kernel + stage1_flatten_kernel",
+                 "fused": "stage1_fused_kernel (classify / scan / flatten interleaved in one persistent launch; + stage1_persistent_kernel "
+                          "as a no-op fallback)"}[kind]
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": prof.get("dram_bytes_per_pass"), "peak_source": f"of {peak_kind}",
                 "kernel": kname, "kernel_ms": round(k_ms, 4), "kernel_ms_second_loop": round(k_ms_check, 4), "algorithmic_bytes_per_launch": int(alg_bytes),

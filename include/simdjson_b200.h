@@ -77,33 +77,43 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *ctx);
 
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
 int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
-/* Force the tile shape: warps per tile in {2,4,8,12,16,24,32} (2 KiB per warp), 0 = choose from the document size. */
+/* Force the tile shape of the PERSISTENT / SPLIT organisations: warps per tile in {2,4,8,16,24} (2 KiB per warp; SPLIT: 8 or
+ * 16), 0 = choose from the document size.  A shape the selected organisation does not have makes the next stage-1 call
+ * return UNEXPECTED_ERROR (never a silently different shape). */
 int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
 /*
  * Force the kernel organisation (tuning / test knob; every choice produces identical results):
- *   AUTO        chosen from the document size: PERSISTENT below 48 MiB and for the chunked host path, SPLIT from 48 MiB,
- *               STREAM from 160 MiB on
- *   TILE        one tile per CTA, look-back by warp 0
- *   PERSISTENT  persistent CTAs, compute warps + scan warp, classify and flatten fused
- *   DATAFLOW    persistent CTAs, classifier warps -> mask ring in shared memory -> flattener warps
- *   SPLIT       two launches: classify (masks + per-chunk carries to HBM), then flatten.  Scratch for SPLIT and STREAM is
- *               allocated on first use, once, for the context's max_len: 0.57 * max_len bytes (mask planes max_len/4,
- *               parked UTF-8 lanes 0.31 * max_len, summaries).  If that fails an explicit choice returns MEMALLOC, the
- *               automatic choice stays with PERSISTENT, which needs none
- *   STREAM      four launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp, two tiny
- *               scan kernels over the chunk summaries, flatten; speculates that no backslash run covers a chunk's whole
- *               32-byte look-behind and, when one does, re-runs the document with PERSISTENT (same results).  UTF-8 of
- *               sparse non-ASCII lanes is validated by a second kernel on an internal stream.  Whole documents only: the
- *               chunked host path uses PERSISTENT.
- * A shape the chosen organisation does not support falls back to PERSISTENT / TILE for that call.
+ *   AUTO        chosen from the document size: PERSISTENT below 8 MiB and for the chunked host path, FUSED from 8 MiB on
+ *   PERSISTENT  persistent CTAs of compute warps + a scan warp over tiles, classify and flatten of a tile fused, decoupled
+ *               look-back between tiles; needs no scratch
+ *   SPLIT       two launches: classify (masks + per-chunk carries to L2 / HBM), then flatten
+ *   STREAM      five launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp, a kernel that
+ *               validates the UTF-8 of sparse non-ASCII lanes on an internal stream, two scan kernels over the chunk
+ *               summaries, flatten
+ *   FUSED       one persistent launch in which every warp alternates between classifying a run of chunks and flattening
+ *               an older run whose block has been scanned meanwhile (decoupled look-back between blocks of 64 chunks);
+ *               UTF-8 of sparse non-ASCII lanes is validated by the classifying warp itself, 32 lanes at a time
+ * STREAM and FUSED resolve the escape state entering a chunk from a bounded look-behind (STREAM: 32 bytes; FUSED: 32
+ * bytes, then a walk back of up to 64 KiB); a longer backslash run makes the PERSISTENT kernel, enqueued behind them on
+ * every call and otherwise returning at once, redo the document (same results).
+ * SPLIT / STREAM / FUSED use scratch in device memory (0.26 bytes per input byte: mask planes, chunk summaries, carry words;
+ * STREAM another 0.31 for parked UTF-8 lanes), allocated with the stream-ordered allocator on first use and grown when a
+ * larger document arrives (no call synchronises for it); sjb200_ctx_reserve allocates it ahead of time.  If the allocation
+ * fails an explicit choice returns MEMALLOC, the automatic choice stays with PERSISTENT.
+ * Values 1 and 3 named two organisations of round 1 that were measured, rejected and removed: UNEXPECTED_ERROR.
  */
 #define SJB200_KERNEL_AUTO 0
-#define SJB200_KERNEL_TILE 1
 #define SJB200_KERNEL_PERSISTENT 2
-#define SJB200_KERNEL_DATAFLOW 3
 #define SJB200_KERNEL_SPLIT 4
 #define SJB200_KERNEL_STREAM 5
+#define SJB200_KERNEL_FUSED 6
 int32_t sjb200_ctx_set_kernel(sjb200_ctx *ctx, int32_t kind);
+/* Allocates the scratch for documents of up to `len` bytes now (flags bit 0: also for the STREAM organisation), so that
+ * no later call has to.  MEMALLOC if it cannot be had. */
+int32_t sjb200_ctx_reserve(sjb200_ctx *ctx, uint64_t len, uint32_t flags);
+/* Chunk size (bytes, >= 4096) of the streaming host path of sjb200_stage1: the document travels to the device in chunks
+ * of this size, each indexed as soon as it has arrived.  Default 32 MiB. */
+int32_t sjb200_ctx_set_chunk_bytes(sjb200_ctx *ctx, uint64_t bytes);
 
 /*
  * Host-to-host drop-in for DomParserImplementation.stage1: copies buf to the device, indexes it, copies the

@@ -23,6 +23,8 @@ SIGNATURES = {
     "sjb200_ctx_set_stream": (_i32, [_vp, _vp]),
     "sjb200_ctx_set_warps": (_i32, [_vp, _i32]),
     "sjb200_ctx_set_kernel": (_i32, [_vp, _i32]),
+    "sjb200_ctx_reserve": (_i32, [_vp, _u64, _u32]),
+    "sjb200_ctx_set_chunk_bytes": (_i32, [_vp, _u64]),
     "sjb200_stage1": (_i32, [_vp, _vp, _u64, _vp, _u64, _pu32, _pi32, _u32]),
     "sjb200_structural_bytes_device_async": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp]),
     "sjb200_document_starts_device_async": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64]),

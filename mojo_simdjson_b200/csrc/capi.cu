@@ -1,4 +1,4 @@
-// capi.cu -- C ABI (include/simdjson_b200.h) over the sm_100a stage-1 kernel: context, buffers, launches.
+// capi.cu -- C ABI (include/simdjson_b200.h) over the sm_100a stage-1 kernels: context, buffers, launches.
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -10,9 +10,9 @@
 #include "../../include/simdjson_b200.h"
 #include "stage1_kernel.cuh"
 #include "stage1_persistent.cuh"
-#include "stage1_dataflow.cuh"
 #include "stage1_split.cuh"
 #include "stage1_stream.cuh"
+#include "stage1_fused.cuh"
 
 #ifndef SJ_K3_FW
 #define SJ_K3_FW 4   // warps (= chunks) per CTA of the flatten kernel (2 and 4: +0.8 % over 8, 16: -2 %)
@@ -24,14 +24,10 @@ namespace {
 
 constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
-// Kernel organisation by document size (device-resident documents; measured on a B200 with the tile shape pick_warps
-// chooses and programmatic dependent launch between the launches of a document, GB/s of input; tools/sizesweep.py):
-//            16 MiB  32 MiB  48 MiB  64 MiB  96 MiB  128 MiB  256 MiB  1 GiB
-//   fused      635     907     996    1091    1172     1212     1284   1348   one persistent kernel
-//   split      658     905    1044    1173    1269     1354     1445   1536   persistent classify + flatten
-//   stream     528     799     995    1023    1153     1295     1542   1794   per-warp classify, 2 scans, flatten
-constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
-constexpr uint64_t STREAM_MIN_BYTES = 160ull << 20;
+// Kernel organisation by document size (device-resident documents; tools/sizesweep.py): the persistent tile kernel for
+// small documents (all 148 SMs get a tile even at a few hundred KiB), the fused kernel (classify / scan / flatten
+// interleaved in one persistent launch) from FUSED_MIN_BYTES on.
+constexpr uint64_t FUSED_MIN_BYTES = 8ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
@@ -45,6 +41,32 @@ inline int32_t cuda_err(cudaError_t e) {
         if (e__ != cudaSuccess) return cuda_err(e__); \
     } while (0)
 
+// Tuning knobs from the environment, read ONCE (first context creation), never on the call path.
+struct Knobs {
+    int pdl = 1;            // SJB200_PDL=0: no programmatic dependent launch between the launches of a document
+    int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
+    int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream|fused
+    uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
+};
+bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24; }
+const Knobs &knobs() {
+    static const Knobs k = [] {
+        Knobs v;
+        if (const char *e = getenv("SJB200_PDL")) v.pdl = atoi(e);
+        if (const char *e = getenv("SJB200_WARPS")) v.warps = valid_warps(atoi(e)) ? atoi(e) : 0;
+        if (const char *e = getenv("SJB200_KERNEL")) {
+            if (strcmp(e, "persist") == 0) v.kernel = SJB200_KERNEL_PERSISTENT;
+            if (strcmp(e, "split") == 0) v.kernel = SJB200_KERNEL_SPLIT;
+            if (strcmp(e, "stream") == 0) v.kernel = SJB200_KERNEL_STREAM;
+            if (strcmp(e, "fused") == 0) v.kernel = SJB200_KERNEL_FUSED;
+        }
+        if (const char *e = getenv("SJB200_CHUNK_MIB"))
+            if (atoi(e) > 0) v.chunk_bytes = (uint64_t)atoi(e) << 20;
+        return v;
+    }();
+    return k;
+}
+
 }  // namespace
 
 struct sjb200_ctx {
@@ -55,28 +77,33 @@ struct sjb200_ctx {
     uint8_t *d_in = nullptr;        // host-path input staging on the device
     uint32_t *d_out = nullptr;      // host-path output on the device
     uint64_t d_out_cap = 0;
-    uint64_t *desc = nullptr;           // look-back descriptors, one 8-byte word per tile
+    uint64_t *desc = nullptr;           // look-back descriptors, one 8-byte word per tile / block
     uint32_t max_tiles = 0;
     uint32_t *ticket = nullptr;
     Stage1Result *h_results = nullptr;  // mapped pinned, RESULT_SLOTS entries
     Stage1Result *d_results = nullptr;  // device alias of h_results
+    int32_t launch_rc[RESULT_SLOTS] = {};   // host-side launch status per result slot (never written by the device)
     uint32_t slot = 0;                  // slot used by the most recent launch
     uint32_t gen = 0;
     int forced_warps = 0;
     int kernel_kind = SJB200_KERNEL_AUTO;  // sjb200_ctx_set_kernel
     int sm_count = 0;
     int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
-    int flow_occ[3] = {0, 0, 0};           // same for the dataflow kernel, NC = 4, 8, 12
     int split_occ[2] = {0, 0};             // same for the classify kernel of the split pair, NW = 8, 16
-    uint64_t *d_masks = nullptr;           // split pair: the two structural mask planes of every 2 KiB chunk
-    uint64_t *d_carry = nullptr;           //             one carry word per chunk
-    uint64_t split_chunks = 0;             //             chunks the two arrays hold (allocated on first use)
-    bool scratch_failed = false;           //             that allocation failed once: automatic choice stays with the fused kernel
+    int stream_occ = 0;                    // same for the stream classify kernel
+    int fused_occ = 0;                     // same for the fused kernel
+    // scratch of the split / stream / fused organisations, sized for `scratch_chunks` 2 KiB chunks (sjb200_ctx_reserve, or
+    // grown on demand with the stream-ordered allocator: no call ever synchronises for it)
+    uint64_t *d_masks = nullptr;           // the two structural mask planes of every chunk (512 B per chunk)
+    uint64_t *d_carry = nullptr;           // one carry word per chunk
+    uint32_t *d_chunk_sum = nullptr;       // 16-byte chunk summaries
+    uint32_t *d_block_sum = nullptr;       // stream pipeline: the same per 4096 chunks
+    uint32_t *d_blk_state = nullptr;       // fused kernel: blk_done[], blk_ready[] and its own look-back descriptors
     uint4 *d_u8_slots = nullptr;           // stream pipeline: parked bit planes of lanes whose UTF-8 validation is deferred
-    uint32_t *d_chunk_sum = nullptr;       // stream pipeline: per-chunk and per-1024-chunk summaries, speculation flag
-    uint32_t *d_block_sum = nullptr;
-    uint32_t *d_spec_flag = nullptr;
-    int stream_occ = 0;                    // resident CTAs per SM of the stream classify kernel
+    uint64_t scratch_chunks = 0;
+    bool scratch_u8 = false;               // d_u8_slots covers scratch_chunks as well (only the stream pipeline needs it)
+    bool scratch_failed = false;           // an allocation failed once: automatic choice stays with the persistent kernel
+    uint32_t *d_spec_flag = nullptr;       // [0] speculation failed, [1] deferred UTF-8 violation (generation valued)
     cudaStream_t aux_stream = nullptr;     // stream pipeline: the deferred UTF-8 lanes are validated here, beside the scan
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -97,22 +124,44 @@ struct sjb200_ctx {
 
 namespace {
 
-template <int WARPS, bool UTF8>
-cudaError_t launch_cfg(const Stage1Params &p, cudaStream_t s) {
-    using Cfg = TileCfg<WARPS>;
-    stage1_kernel<WARPS, UTF8><<<p.tile_end - p.tile_begin, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
-}
-template <int WARPS>
-cudaError_t prepare_cfg() {
-    using Cfg = TileCfg<WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(stage1_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    cudaFuncSetAttribute(stage1_kernel<WARPS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_kernel<WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+template <typename K>
+cudaError_t prepare_kernel(K kernel_utf8, K kernel_plain, int threads, int smem, int *occ) {
+    cudaError_t e = cudaFuncSetAttribute(kernel_utf8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(kernel_utf8, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(kernel_plain, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int a = 0, b = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kernel_utf8, threads, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel_plain, threads, smem);
+    *occ = a < b ? a : b;
+    if (*occ < 1) *occ = 1;
     return e;
 }
+template <int NW>
+cudaError_t prepare_persist(int *occ) {
+    using Cfg = PersistCfg<NW>;
+    return prepare_kernel(stage1_persistent_kernel<NW, true>, stage1_persistent_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
+}
+template <int NW>
+cudaError_t prepare_split(int *occ) {
+    using Cfg = SplitCfg<NW>;
+    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return prepare_kernel(stage1_classify_kernel<NW, true>, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
+}
+#ifndef SJ_STREAM_NW
+#define SJ_STREAM_NW 8
+#endif
+constexpr int STREAM_NW = SJ_STREAM_NW;
+constexpr int FUSED_NW = SJ_FUSED_NW;
+cudaError_t prepare_stream(int *occ) {
+    using Cfg = StreamCfg<STREAM_NW>;
+    return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
+}
+cudaError_t prepare_fused(int *occ) {
+    using Cfg = FusedCfg<FUSED_NW>;
+    return prepare_kernel(stage1_fused_kernel<FUSED_NW, true>, stage1_fused_kernel<FUSED_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
+}
+
 template <int NW, bool UTF8>
 cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = PersistCfg<NW>;
@@ -120,44 +169,6 @@ cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) 
     const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
     stage1_persistent_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
-}
-template <int NW>
-cudaError_t prepare_persist(int *occ) {
-    using Cfg = PersistCfg<NW>;
-    cudaError_t e = cudaFuncSetAttribute(stage1_persistent_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stage1_persistent_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    cudaFuncSetAttribute(stage1_persistent_kernel<NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_persistent_kernel<NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int a = 0, b = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_persistent_kernel<NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_persistent_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    *occ = a < b ? a : b;
-    if (*occ < 1) *occ = 1;
-    return e;
-}
-template <int NC, bool UTF8>
-cudaError_t launch_flow(const Stage1Params &p, cudaStream_t s, int max_ctas) {
-    using Cfg = FlowCfg<NC>;
-    const unsigned span = p.tile_end - p.tile_begin;
-    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
-    stage1_dataflow_kernel<NC, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
-}
-template <int NC>
-cudaError_t prepare_flow(int *occ) {
-    using Cfg = FlowCfg<NC>;
-    cudaError_t e = cudaFuncSetAttribute(stage1_dataflow_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stage1_dataflow_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    cudaFuncSetAttribute(stage1_dataflow_kernel<NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_dataflow_kernel<NC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int a = 0, b = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_dataflow_kernel<NC, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_dataflow_kernel<NC, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    *occ = a < b ? a : b;
-    if (*occ < 1) *occ = 1;
-    return e;
 }
 // Launch `kernel` so that it may be scheduled while the previous kernel of the stream drains (programmatic dependent
 // launch); the kernel itself waits for its predecessor (griddepcontrol.wait) before it reads anything.
@@ -175,14 +186,6 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned b
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-bool use_pdl() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SJB200_PDL");
-        v = e ? atoi(e) : 1;
-    }
-    return v != 0;
-}
 
 template <int NW, bool UTF8>
 cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
@@ -194,12 +197,8 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     if (e != cudaSuccess) return e;
     constexpr int FW = SJ_K3_FW;
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
-    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, use_pdl(), p, c0, c1);
+    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
 }
-#ifndef SJ_STREAM_NW
-#define SJ_STREAM_NW 8
-#endif
-constexpr int STREAM_NW = SJ_STREAM_NW;
 template <bool UTF8>
 cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = StreamCfg<STREAM_NW>;
@@ -208,7 +207,7 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
     stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
     cudaError_t e = cudaGetLastError();
-    const bool pdl = use_pdl();
+    const bool pdl = knobs().pdl != 0;
     if (e == cudaSuccess && UTF8) {
         // The lanes whose UTF-8 validation the classify kernel deferred: on the context's second stream, beside the two
         // (latency-bound) scan launches and the start of the flatten kernel.  Nothing on `s` needs its result before the
@@ -231,47 +230,19 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     if (e == cudaSuccess && UTF8) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch
     return e;
 }
-cudaError_t prepare_stream(int *occ) {
-    using Cfg = StreamCfg<STREAM_NW>;
-    cudaError_t e = cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_stream_classify_kernel<STREAM_NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int a = 0, b = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_stream_classify_kernel<STREAM_NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    *occ = a < b ? a : b;
-    if (*occ < 1) *occ = 1;
-    return e;
+template <bool UTF8>
+cudaError_t launch_fused(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = FusedCfg<FUSED_NW>;
+    const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
+    const unsigned want = (nchunks + FUSED_NW * TICKET_CHUNKS - 1) / (FUSED_NW * TICKET_CHUNKS);
+    const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
+    stage1_fused_kernel<FUSED_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
+    return cudaGetLastError();
 }
-template <int NW>
-cudaError_t prepare_split(int *occ) {
-    using Cfg = SplitCfg<NW>;
-    cudaError_t e = cudaFuncSetAttribute(stage1_classify_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    cudaFuncSetAttribute(stage1_classify_kernel<NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_classify_kernel<NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int a = 0, b = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage1_classify_kernel<NW, true>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES);
-    *occ = a < b ? a : b;
-    if (*occ < 1) *occ = 1;
-    return e;
-}
-bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32; }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (c->forced_warps) return c->forced_warps;
-    static int env = -1;
-    if (env < 0) {
-        const char *e = getenv("SJB200_WARPS");
-        env = e ? atoi(e) : 0;
-        if (!valid_warps(env)) env = 0;
-    }
-    if (env) return env;
+    if (knobs().warps) return knobs().warps;
     // small documents: smaller tiles so that the work spreads over all 148 SMs
     if (alen >= (uint64_t)64 << 20) return 16;
     if (alen >= (uint64_t)148 * 4 * 16384) return 8;
@@ -283,30 +254,62 @@ int pick_warps(const sjb200_ctx *c, uint64_t alen) {
 // everything) or, on the streaming host path, by several launches over consecutive tile ranges sharing the generation.
 struct DocPlan {
     Stage1Params p;
-    int warps;
-    bool persist;
-    bool flow;
-    bool split;
-    bool stream;
+    uint64_t *fdesc; // look-back descriptors of the fused kernel's blocks (its fallback, the persistent kernel, keeps p.desc)
+    int warps;       // tile shape of the persistent kernel (also the exact fallback of the speculating organisations)
+    int kind;        // SJB200_KERNEL_PERSISTENT / SPLIT / STREAM / FUSED
     bool utf8;
 };
 
-void free_split_scratch(sjb200_ctx *c) {
-    cudaFree(c->d_masks);
-    cudaFree(c->d_carry);
-    cudaFree(c->d_chunk_sum);
-    cudaFree(c->d_block_sum);
-    cudaFree(c->d_spec_flag);
-    cudaFree(c->d_u8_slots);
-    c->d_u8_slots = nullptr;
+void free_scratch(sjb200_ctx *c, cudaStream_t s) {
+    // stream ordered: kernels already enqueued on `s` keep their buffers until they have run
+    if (c->d_masks) cudaFreeAsync(c->d_masks, s);
+    if (c->d_carry) cudaFreeAsync(c->d_carry, s);
+    if (c->d_chunk_sum) cudaFreeAsync(c->d_chunk_sum, s);
+    if (c->d_block_sum) cudaFreeAsync(c->d_block_sum, s);
+    if (c->d_blk_state) cudaFreeAsync(c->d_blk_state, s);
+    if (c->d_u8_slots) cudaFreeAsync(c->d_u8_slots, s);
     c->d_masks = c->d_carry = nullptr;
-    c->d_chunk_sum = c->d_block_sum = c->d_spec_flag = nullptr;
-    c->split_chunks = 0;
+    c->d_chunk_sum = c->d_block_sum = c->d_blk_state = nullptr;
+    c->d_u8_slots = nullptr;
+    c->scratch_chunks = 0;
+    c->scratch_u8 = false;
+}
+
+// Scratch for documents of up to `chunks` 2 KiB chunks (0.26 bytes per input byte: mask planes len/4, summaries and carry
+// words; the stream pipeline's parked UTF-8 lanes add 0.31 bytes per input byte and are allocated only when it is used).
+// Grows geometrically; allocation and release are stream ordered (cudaMallocAsync), so an enqueue never synchronises.
+cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, bool need_u8, cudaStream_t s) {
+    if (chunks <= c->scratch_chunks && (!need_u8 || c->scratch_u8)) return cudaSuccess;
+    uint64_t n = chunks + 64;
+    if (n < c->scratch_chunks) n = c->scratch_chunks;
+    if (chunks > c->scratch_chunks && n < c->scratch_chunks * 3 / 2) n = c->scratch_chunks * 3 / 2;
+    const uint64_t max_chunks = (c->max_len + 16) / 2048 + 64;
+    if (n > max_chunks) n = max_chunks > chunks + 64 ? max_chunks : chunks + 64;
+    const bool u8 = need_u8 || c->scratch_u8;
+    free_scratch(c, s);
+    const uint64_t nblk = n / BLOCK_CHUNKS + 2;
+    cudaError_t e = cudaMallocAsync(&c->d_masks, n * 512, s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_carry, n * 8, s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_chunk_sum, n * 16, s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16, s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_blk_state, nblk * 16, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_blk_state, 0, nblk * 16, s);
+    if (e == cudaSuccess && u8) e = cudaMallocAsync(&c->d_u8_slots, n * (size_t)(U8_SLOTS * U8_SLOT_VECTORS * 16), s);
+    if (e != cudaSuccess) {
+        free_scratch(c, s);
+        cudaGetLastError();
+        return e;
+    }
+    c->scratch_chunks = n;
+    c->scratch_u8 = u8;
+    return cudaSuccess;
 }
 
 int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t len, uint32_t *d_idx, uint64_t cap,
                       uint32_t flags, uint32_t slot, int32_t *d_status, bool whole_document = true) {
     Stage1Params &p = d.p;
+    memset(&p, 0, sizeof p);
+    d.fdesc = nullptr;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
     p.mis = (uint32_t)(addr & 15u);
     p.abase = d_buf - p.mis;
@@ -318,91 +321,72 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     p.result = c->d_results + slot;
     p.dev_status = d_status;
     p.trace = c->d_trace;
-    p.progress = nullptr;
     c->gen = (c->gen + 1) & GEN_MASK;
-    if (c->gen == 0) {  // the 20-bit generation wrapped: clear descriptors and tickets once (stream ordered), restart at 1
+    if (c->gen == 0) {  // the 20-bit generation wrapped: clear everything generation tagged once (stream ordered), restart at 1
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
         cudaMemsetAsync(c->ticket, 0, 256, c->stream);
-        if (c->d_spec_flag) cudaMemsetAsync(c->d_spec_flag, 0, 256, c->stream);
+        cudaMemsetAsync(c->d_spec_flag, 0, 256, c->stream);
+        if (c->d_blk_state) cudaMemsetAsync(c->d_blk_state, 0, (c->scratch_chunks / BLOCK_CHUNKS + 2) * 16, c->stream);
         c->gen = 1;
     }
     p.gen = c->gen;
     p.flags = flags;
-    d.warps = pick_warps(c, p.alen);
-    static int env_kind = -1;
-    if (env_kind < 0) {
-        const char *e = getenv("SJB200_KERNEL");
-        env_kind = SJB200_KERNEL_AUTO;
-        if (e && strcmp(e, "tile") == 0) env_kind = SJB200_KERNEL_TILE;
-        if (e && strcmp(e, "persist") == 0) env_kind = SJB200_KERNEL_PERSISTENT;
-        if (e && strcmp(e, "flow") == 0) env_kind = SJB200_KERNEL_DATAFLOW;
-        if (e && strcmp(e, "split") == 0) env_kind = SJB200_KERNEL_SPLIT;
-        if (e && strcmp(e, "stream") == 0) env_kind = SJB200_KERNEL_STREAM;
-    }
-    int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : env_kind;
+    d.utf8 = !(flags & SJB200_FLAG_NO_UTF8);
+    int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : knobs().kernel;
     const bool auto_kind = kind == SJB200_KERNEL_AUTO;
-    if (auto_kind) {
-        kind = SJB200_KERNEL_PERSISTENT;
-        if (whole_document && !c->scratch_failed && p.alen >= SPLIT_MIN_BYTES) kind = SJB200_KERNEL_SPLIT;
-        if (whole_document && !c->scratch_failed && p.alen >= STREAM_MIN_BYTES) kind = SJB200_KERNEL_STREAM;
+    if (auto_kind) kind = (whole_document && !c->scratch_failed && p.alen >= FUSED_MIN_BYTES) ? SJB200_KERNEL_FUSED : SJB200_KERNEL_PERSISTENT;
+    if (!whole_document) kind = SJB200_KERNEL_PERSISTENT;   // ranges of a document (streaming host path): look-back across launches
+    d.warps = pick_warps(c, p.alen);
+    if (kind == SJB200_KERNEL_SPLIT && d.warps != 8 && d.warps != 16) {
+        // the split pair exists for 8- and 16-warp tiles only: an explicit shape it does not have is an error, never a silent
+        // substitution of another kernel shape
+        if (c->forced_warps || knobs().warps) return SJB200_UNEXPECTED_ERROR;
+        d.warps = p.alen >= ((uint64_t)64 << 20) ? 16 : 8;
     }
-    d.stream = kind == SJB200_KERNEL_STREAM;
-    if (d.stream && d.warps > 24) d.warps = 16;   // shape of the fallback (persistent) launch
-    d.split = kind == SJB200_KERNEL_SPLIT && (d.warps == 8 || d.warps == 16);
-    d.flow = kind == SJB200_KERNEL_DATAFLOW && (d.warps == 4 || d.warps == 8 || d.warps == 12);
-    d.persist = d.stream || d.split || d.flow || (kind != SJB200_KERNEL_TILE && d.warps <= 24);
+    if (!valid_warps(d.warps)) return SJB200_UNEXPECTED_ERROR;
+    const uint64_t chunks = (p.alen + 2047) / 2048;
+    if (kind != SJB200_KERNEL_PERSISTENT) {
+        const cudaError_t e = ensure_scratch(c, chunks + 32, kind == SJB200_KERNEL_STREAM && d.utf8, c->stream);
+        if (e != cudaSuccess) {
+            if (!auto_kind) return SJB200_MEMALLOC;   // the caller asked for this organisation explicitly
+            c->scratch_failed = true;                 // chosen automatically: the persistent kernel needs no scratch
+            kind = SJB200_KERNEL_PERSISTENT;
+        }
+    }
+    d.kind = kind;
     const uint64_t tile = (uint64_t)d.warps * 2048;
     const uint64_t ntiles = (p.alen + tile - 1) / tile;
     if (ntiles > c->max_tiles) return SJB200_CAPACITY;
     p.ntiles = (uint32_t)ntiles;
     p.tile_begin = 0;
     p.tile_end = p.ntiles;
-    // ticket counters: [0],[1] alternate between successive persistent launches, [2] serves the one-tile-per-CTA kernel
-    p.ticket = d.persist ? c->ticket : c->ticket + 2;
-    d.utf8 = !(flags & SJB200_FLAG_NO_UTF8);
-    p.masks = nullptr;
-    p.carry = nullptr;
-    p.chunk_sum = nullptr;
-    p.block_sum = nullptr;
-    p.spec_flag = nullptr;
-    p.u8_slots = nullptr;
-    if (d.split || d.stream) {
-        const uint64_t chunks = ntiles * (uint64_t)d.warps;
-        if (chunks > c->split_chunks) {  // first use (or a larger document than before): (re)allocate, stream ordered
-            cudaStreamSynchronize(c->stream);
-            free_split_scratch(c);
-            const uint64_t want = (c->max_len + 16) / 2048 + 64;
-            const uint64_t n = chunks > want ? chunks : want;
-            if (cudaMalloc(&c->d_masks, n * 512) != cudaSuccess || cudaMalloc(&c->d_carry, n * 8) != cudaSuccess ||
-                cudaMalloc(&c->d_chunk_sum, n * 16) != cudaSuccess || cudaMalloc(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16) != cudaSuccess ||
-                cudaMalloc(&c->d_spec_flag, 256) != cudaSuccess || cudaMemset(c->d_spec_flag, 0, 256) != cudaSuccess ||
-                cudaMalloc(&c->d_u8_slots, n * (size_t)(U8_SLOTS * U8_SLOT_VECTORS * 16)) != cudaSuccess) {
-                free_split_scratch(c);
-                cudaGetLastError();
-                if (!auto_kind) return SJB200_MEMALLOC;   // the caller asked for this organisation explicitly
-                // chosen automatically: the fused kernel needs no scratch; do not try again for this context
-                c->scratch_failed = true;
-                d.split = d.stream = false;
-                d.warps = pick_warps(c, p.alen);
-                d.persist = d.warps <= 24;
-                const uint64_t t2 = (uint64_t)d.warps * 2048;
-                p.ntiles = (uint32_t)((p.alen + t2 - 1) / t2);
-                p.tile_end = p.ntiles;
-                p.ticket = d.persist ? c->ticket : c->ticket + 2;
-                return SJB200_SUCCESS;
-            }
-            c->split_chunks = n;
-        }
+    p.ticket = c->ticket;   // [0],[1] alternate between persistent launches, [3..5] serve the stream / fused kernels
+    if (kind != SJB200_KERNEL_PERSISTENT) {
         p.masks = c->d_masks;
         p.carry = c->d_carry;
-        if (d.stream) {
-            p.chunk_sum = c->d_chunk_sum;
-            p.block_sum = c->d_block_sum;
-            p.spec_flag = c->d_spec_flag;
-            p.u8_slots = c->d_u8_slots;
-        }
+        p.chunk_sum = c->d_chunk_sum;
+        p.block_sum = c->d_block_sum;
+        p.u8_slots = c->d_u8_slots;
+        const uint64_t nblk = c->scratch_chunks / BLOCK_CHUNKS + 2;
+        p.blk_done = c->d_blk_state;
+        p.blk_ready = c->d_blk_state + nblk;
+        d.fdesc = reinterpret_cast<uint64_t *>(c->d_blk_state + 2 * nblk);
     }
+    if (kind == SJB200_KERNEL_STREAM || kind == SJB200_KERNEL_FUSED) p.spec_flag = c->d_spec_flag;
     return SJB200_SUCCESS;
+}
+
+cudaError_t launch_persistent_range(sjb200_ctx *c, const Stage1Params &p, int warps, bool utf8, cudaStream_t stream) {
+    const int idx = warps == 24 ? 4 : (warps == 16 ? 3 : (warps == 8 ? 2 : (warps == 4 ? 1 : 0)));
+    const int max_ctas = c->sm_count * c->persist_occ[idx];
+    switch (warps) {
+    case 24: return utf8 ? launch_persist<24, true>(p, stream, max_ctas) : launch_persist<24, false>(p, stream, max_ctas);
+    case 16: return utf8 ? launch_persist<16, true>(p, stream, max_ctas) : launch_persist<16, false>(p, stream, max_ctas);
+    case 8: return utf8 ? launch_persist<8, true>(p, stream, max_ctas) : launch_persist<8, false>(p, stream, max_ctas);
+    case 4: return utf8 ? launch_persist<4, true>(p, stream, max_ctas) : launch_persist<4, false>(p, stream, max_ctas);
+    case 2: return utf8 ? launch_persist<2, true>(p, stream, max_ctas) : launch_persist<2, false>(p, stream, max_ctas);
+    default: return cudaErrorInvalidValue;   // a shape that is not instantiated is an error, never another shape
+    }
 }
 
 // launch the tiles [tile_begin, tile_end) of a planned document on `stream`
@@ -411,53 +395,44 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     p.tile_begin = tile_begin;
     p.tile_end = tile_end;
     p.progress = progress;
-    p.ticket_sel = d.persist ? (c->launch_seq++ & 1u) : 0u;  // only persistent launches alternate the two counters
-    const int warps = d.warps;
     const bool utf8 = d.utf8;
-    cudaError_t e;
     const bool whole = tile_begin == 0 && tile_end == d.p.ntiles;
-    if (!(d.stream && whole)) p.spec_flag = nullptr;   // a partial range is indexed by the persistent kernel alone
-    if (d.stream && whole) {
-        // speculative pipeline, then the persistent kernel as its exact fallback (returns at once unless the flag was raised)
-        e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(c, p, stream, c->sm_count * c->stream_occ);
-        c->launches += utf8 ? 5 : 4;
-    }
-    if (d.stream && whole && e != cudaSuccess) {
-        cudaMemsetAsync(c->ticket, 0, 256, stream);   // a half-issued pipeline may leave its chunk counter non-zero
-        return cuda_err(e);
-    } else if (d.split) {
-        const int max_ctas = c->sm_count * c->split_occ[warps == 16 ? 1 : 0];
-        if (warps == 16) e = utf8 ? launch_split<16, true>(p, stream, max_ctas) : launch_split<16, false>(p, stream, max_ctas);
-        else e = utf8 ? launch_split<8, true>(p, stream, max_ctas) : launch_split<8, false>(p, stream, max_ctas);
-        c->launches++;
-    } else if (d.flow && !d.stream) {
-        const int max_ctas = c->sm_count * c->flow_occ[warps == 12 ? 2 : (warps == 8 ? 1 : 0)];
-        switch (warps) {
-        case 12: e = utf8 ? launch_flow<12, true>(p, stream, max_ctas) : launch_flow<12, false>(p, stream, max_ctas); break;
-        case 8: e = utf8 ? launch_flow<8, true>(p, stream, max_ctas) : launch_flow<8, false>(p, stream, max_ctas); break;
-        default: e = utf8 ? launch_flow<4, true>(p, stream, max_ctas) : launch_flow<4, false>(p, stream, max_ctas); break;
+    cudaError_t e = cudaSuccess;
+    const bool speculating = (d.kind == SJB200_KERNEL_STREAM || d.kind == SJB200_KERNEL_FUSED) && whole;
+    if (speculating) {
+        if (d.kind == SJB200_KERNEL_STREAM) {
+            e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(c, p, stream, c->sm_count * c->stream_occ);
+            c->launches += utf8 ? 5 : 4;
+        } else {
+            Stage1Params pf = p;
+            pf.desc = d.fdesc;
+            e = utf8 ? launch_fused<true>(pf, stream, c->sm_count * c->fused_occ) : launch_fused<false>(pf, stream, c->sm_count * c->fused_occ);
+            c->launches += 1;
         }
-    } else if (d.persist) {
-        const int idx = warps == 24 ? 4 : (warps == 16 ? 3 : (warps == 8 ? 2 : (warps == 4 ? 1 : 0)));
-        const int max_ctas = c->sm_count * c->persist_occ[idx];
-        switch (warps) {
-        case 24: e = utf8 ? launch_persist<24, true>(p, stream, max_ctas) : launch_persist<24, false>(p, stream, max_ctas); break;
-        case 16: e = utf8 ? launch_persist<16, true>(p, stream, max_ctas) : launch_persist<16, false>(p, stream, max_ctas); break;
-        case 8: e = utf8 ? launch_persist<8, true>(p, stream, max_ctas) : launch_persist<8, false>(p, stream, max_ctas); break;
-        case 4: e = utf8 ? launch_persist<4, true>(p, stream, max_ctas) : launch_persist<4, false>(p, stream, max_ctas); break;
-        default: e = utf8 ? launch_persist<2, true>(p, stream, max_ctas) : launch_persist<2, false>(p, stream, max_ctas); break;
-        }
+        // ... then the persistent kernel as the exact fallback: returns at once unless a chunk raised the speculation flag
     } else {
-        switch (warps) {
-        case 32: e = utf8 ? launch_cfg<32, true>(p, stream) : launch_cfg<32, false>(p, stream); break;
-        case 16: e = utf8 ? launch_cfg<16, true>(p, stream) : launch_cfg<16, false>(p, stream); break;
-        case 8: e = utf8 ? launch_cfg<8, true>(p, stream) : launch_cfg<8, false>(p, stream); break;
-        case 4: e = utf8 ? launch_cfg<4, true>(p, stream) : launch_cfg<4, false>(p, stream); break;
-        default: e = utf8 ? launch_cfg<2, true>(p, stream) : launch_cfg<2, false>(p, stream); break;
+        p.spec_flag = nullptr;   // the persistent kernel alone indexes this range
+    }
+    if (e == cudaSuccess) {
+        p.ticket_sel = c->launch_seq & 1u;   // persistent launches alternate two ticket counters
+        if (d.kind == SJB200_KERNEL_SPLIT && whole) {
+            const int max_ctas = c->sm_count * c->split_occ[d.warps == 16 ? 1 : 0];
+            if (d.warps == 16) e = utf8 ? launch_split<16, true>(p, stream, max_ctas) : launch_split<16, false>(p, stream, max_ctas);
+            else e = utf8 ? launch_split<8, true>(p, stream, max_ctas) : launch_split<8, false>(p, stream, max_ctas);
+            c->launches += 2;
+        } else {
+            e = launch_persistent_range(c, p, d.warps, utf8, stream);
+            c->launches += 1;
         }
     }
-    c->launches++;
-    return cuda_err(e);
+    if (e != cudaSuccess) {
+        // a half-issued document may leave a ticket counter non-zero or skip the reset of the other one
+        cudaMemsetAsync(c->ticket, 0, 256, stream);
+        cudaGetLastError();
+        return cuda_err(e);
+    }
+    c->launch_seq++;   // only a launch that really went out flips the ticket counters
+    return SJB200_SUCCESS;
 }
 
 // enqueue one stage-1 kernel over a whole document; the result lands in result slot `slot`
@@ -690,28 +665,20 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     for (int k = 0; k < sjb200_ctx::MAX_CHUNKS && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_progress, 4 * sjb200_ctx::MAX_CHUNKS, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->d_progress, c->h_progress, 0);
-    if (e == cudaSuccess) {
-        const char *cb = getenv("SJB200_CHUNK_MIB");
-        if (cb && atoi(cb) > 0) c->chunk_bytes = (uint64_t)atoi(cb) << 20;
-    }
+    c->chunk_bytes = knobs().chunk_bytes;
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = prepare_cfg<2>();
-    if (e == cudaSuccess) e = prepare_cfg<4>();
-    if (e == cudaSuccess) e = prepare_cfg<8>();
-    if (e == cudaSuccess) e = prepare_cfg<16>();
-    if (e == cudaSuccess) e = prepare_cfg<32>();
     if (e == cudaSuccess) e = prepare_persist<2>(&c->persist_occ[0]);
     if (e == cudaSuccess) e = prepare_persist<4>(&c->persist_occ[1]);
     if (e == cudaSuccess) e = prepare_persist<8>(&c->persist_occ[2]);
     if (e == cudaSuccess) e = prepare_persist<16>(&c->persist_occ[3]);
     if (e == cudaSuccess) e = prepare_persist<24>(&c->persist_occ[4]);
-    if (e == cudaSuccess) e = prepare_flow<4>(&c->flow_occ[0]);
-    if (e == cudaSuccess) e = prepare_flow<8>(&c->flow_occ[1]);
-    if (e == cudaSuccess) e = prepare_flow<12>(&c->flow_occ[2]);
     if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
     if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
     if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
+    if (e == cudaSuccess) e = prepare_fused(&c->fused_occ);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_spec_flag, 256);
+    if (e == cudaSuccess) e = cudaMemset(c->d_spec_flag, 0, 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -737,7 +704,11 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     cudaFree(c->ticket);
     cudaFree(c->d_split);
     cudaFree(c->d_trace);
-    free_split_scratch(c);
+    cudaFree(c->d_spec_flag);
+    if (c->stream) {
+        free_scratch(c, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_progress) cudaFreeHost(c->h_progress);
     for (int k = 0; k < sjb200_ctx::MAX_CHUNKS; k++)
@@ -764,7 +735,9 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *c, void *cuda_stream) {
 
 int32_t sjb200_ctx_set_kernel(sjb200_ctx *c, int32_t kind) {
     if (!c) return SJB200_UNINITIALIZED;
-    if (kind < SJB200_KERNEL_AUTO || kind > SJB200_KERNEL_STREAM) return SJB200_UNEXPECTED_ERROR;
+    if (kind != SJB200_KERNEL_AUTO && kind != SJB200_KERNEL_PERSISTENT && kind != SJB200_KERNEL_SPLIT && kind != SJB200_KERNEL_STREAM &&
+        kind != SJB200_KERNEL_FUSED)
+        return SJB200_UNEXPECTED_ERROR;
     c->kernel_kind = kind;
     return SJB200_SUCCESS;
 }
@@ -773,6 +746,24 @@ int32_t sjb200_ctx_set_warps(sjb200_ctx *c, int32_t warps) {
     if (!c) return SJB200_UNINITIALIZED;
     if (warps != 0 && !valid_warps(warps)) return SJB200_UNEXPECTED_ERROR;
     c->forced_warps = warps;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_reserve(sjb200_ctx *c, uint64_t len, uint32_t flags) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (len > 0xFFFFFFFFull || len > c->max_len) return SJB200_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    const bool u8 = (flags & 1u) != 0;   // bit 0: also the stream pipeline's parked UTF-8 lanes
+    const cudaError_t e = ensure_scratch(c, (len + 15 + 2047) / 2048 + 32, u8, c->stream);
+    if (e != cudaSuccess) return SJB200_MEMALLOC;
+    c->scratch_failed = false;
+    return SJB200_SUCCESS;
+}
+
+int32_t sjb200_ctx_set_chunk_bytes(sjb200_ctx *c, uint64_t bytes) {
+    if (!c) return SJB200_UNINITIALIZED;
+    if (bytes < 4096) return SJB200_UNEXPECTED_ERROR;
+    c->chunk_bytes = bytes;
     return SJB200_SUCCESS;
 }
 
@@ -1026,10 +1017,8 @@ int32_t sjb200_batch_run_device_async(sjb200_ctx *c, const uint8_t *d_buf, const
         else if (len > 0xFFFFFFFFull || len > c->max_len || next <= idx_offsets[s] || next > idx_capacity) rc = SJB200_CAPACITY;
         else rc = enqueue(c, d_buf + beg, len, d_idx + idx_offsets[s], next - idx_offsets[s], flags, i,
                           d_status ? d_status + 2 * i : nullptr);
-        c->h_results[i].reserved[0] = (uint32_t)rc;  // host-side launch status of this slot
+        c->launch_rc[i] = rc;   // host-side launch status of this slot; the device-written slot itself is never touched here
         if (rc != SJB200_SUCCESS) {
-            c->h_results[i].error = rc;
-            c->h_results[i].n_valid = 0;
             if (d_status) {
                 const int32_t pair[2] = {rc, 0};
                 cudaMemcpyAsync(d_status + 2 * i, pair, sizeof pair, cudaMemcpyHostToDevice, c->stream);
@@ -1052,8 +1041,12 @@ int32_t sjb200_batch_run_device(sjb200_ctx *c, const uint8_t *d_buf, const uint6
     worst = SJB200_SUCCESS;
     for (uint32_t i = 0; i < count; i++) {
         const uint32_t s = first + i;
-        const Stage1Result r = c->h_results[i];
-        const bool launched = r.reserved[0] == SJB200_SUCCESS || r.reserved[0] == 0;
+        Stage1Result r = c->h_results[i];
+        const bool launched = c->launch_rc[i] == SJB200_SUCCESS;
+        if (!launched) {   // nothing ran for this segment: the slot holds an older result
+            r.error = c->launch_rc[i];
+            r.n_valid = 0;
+        }
         if (seg_errors) seg_errors[s] = r.error;
         if (seg_counts) seg_counts[s] = r.n_valid ? r.n : 0;
         if (seg_utf8) seg_utf8[s] = (!launched || (flags & SJB200_FLAG_NO_UTF8)) ? -1 : r.utf8_error;

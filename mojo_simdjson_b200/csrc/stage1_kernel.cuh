@@ -1,21 +1,16 @@
-// stage1_kernel.cuh -- the sm_100a stage-1 kernel: one launch turns input bytes into the ordered uint32
-// structural index array + verdict.  Replaces JsonStructuralIndexer.index/step/next/finish and BitIndexer
+// stage1_kernel.cuh -- device code shared by every organisation of the sm_100a stage-1 indexer: PTX helpers
+// (mbarrier, cp.async.bulk, relaxed descriptor loads / stores), the decoupled look-back over generation-tagged tile
+// descriptors, phase 1 of a warp (2 KiB of input -> dual structural masks + warp summary), the verdict (finish()),
+// and the bitmask -> index flattening pieces.  Replaces JsonStructuralIndexer.index/step/next/finish and BitIndexer
 // (reference generic/stage1/json_structural_indexer.mojo:33-58,81-186) and the scanners they call.
 //
 // Work decomposition
 //   lane  : 64 consecutive bytes (one 64-bit word of every mask)
-//   warp  : 2 KiB; carries between lanes resolved with ballots
-//   CTA   : WARPS x 2 KiB = one tile, loaded by ONE bulk async copy (cp.async.bulk -> UBLKCP) into shared
-//           memory behind an mbarrier; the same shared memory is reused to stage the tile's indexes so the
-//           global index write is coalesced 16-byte stores
-//   grid  : one CTA per tile, tile ids handed out by an atomic ticket so that a tile only ever waits for
-//           tiles that are already running (forward progress of the look-back)
+//   warp  : 2 KiB chunk; carries between lanes resolved with ballots
 // Carries (stage1_core.cuh): "escaped" and "previous scalar" are resolved locally from the bytes just before a
-// warp / tile (they sit in shared memory; the tile brings a 16-byte halo).  The in-string parity is the only
-// global carry: every lane produces its structural bits for BOTH values of it, every tile publishes
-// {quote parity, count if it starts outside a string, count if inside, error flags for both} in one 8-byte,
-// generation-tagged descriptor, and ONE decoupled look-back yields both the parity entering the tile and the
-// output cursor.
+// warp / tile.  The in-string parity is the only global carry: every lane produces its structural bits for BOTH
+// values of it, every tile / chunk publishes {quote parity, count if it starts outside a string, count if inside,
+// error flags for both}, and ONE ordered scan yields both the parity entering it and the output cursor.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +24,6 @@
 #ifndef SJ_NSLEEP
 #define SJ_NSLEEP 20
 #endif
-#ifndef SJ_FLOWREG8
-#define SJ_FLOWREG8 56
-#endif
 #ifndef SJ_REG8
 #define SJ_REG8 56
 #endif
@@ -40,12 +32,6 @@
 #endif
 #ifndef SJ_REG24
 #define SJ_REG24 72
-#endif
-#ifndef SJ_SKIP_FLUSH
-#define SJ_SKIP_FLUSH 0
-#endif
-#ifndef SJ_SKIP_COMPUTE
-#define SJ_SKIP_COMPUTE 0
 #endif
 #ifndef SJ_TRACE
 #define SJ_TRACE 0
@@ -101,6 +87,8 @@ struct Stage1Params {
     uint32_t *block_sum;    // stream pipeline only: the same per 1024 chunks
     uint32_t *spec_flag;    // stream pipeline: == gen once a chunk could not resolve its escape carry locally.  Persistent
                             // kernel: if non-null, run only when *spec_flag == gen (it is the exact fallback)
+    uint32_t *blk_done;     // fused kernel: chunks classified so far per block of 64 chunks (returns to 0 when the block is scanned)
+    uint32_t *blk_ready;    // fused kernel: == gen once the block's carry words are written
     uint64_t *trace;        // debug builds (-DSJ_TRACE=1): 16 x u64 of timestamps per tile, else unused
 };
 
@@ -343,14 +331,17 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
 }
 
 // DEFER_U8: when only a few lanes of the warp hold (or directly follow) bytes >= 0x80, do not validate UTF-8 here -- the
-// whole warp would pay ~75 ALU instructions for them -- but report those lanes; stage1_utf8_lanes_kernel (stage1_stream.cuh)
-// validates exactly those lanes, 32 of them per warp.
+// whole warp would pay ~75 ALU instructions for them -- but park those lanes (16 bit-plane words, the 4 bytes before the
+// lane, its end-of-document bit: 80 B) and report them; they are validated later 32 at a time:
+//   DEFER_U8 == 1 : parked in global memory, validated by stage1_utf8_lanes_kernel (stage1_stream.cuh)
+//   DEFER_U8 == 2 : parked in the warp's own shared-memory slots, validated by the same warp at the end of its run of
+//                   chunks (stage1_fused.cuh); `u8_slots` then points at the first free slot
 #ifndef SJ_U8_DEFER_MAX
 #define SJ_U8_DEFER_MAX 8
 #endif
-template <bool UTF8, bool DEFER_U8 = false>
+template <bool UTF8, int DEFER_U8 = 0>
 __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P,
-                                             uint4 *u8_slots = nullptr /* DEFER_U8: this chunk's 8 slots of 5 uint4 */) {
+                                             uint4 *u8_slots = nullptr /* DEFER_U8: 8 free slots of 5 uint4 */) {
     LaneMasks m;
     uint32_t u8err = 0;
     r.u8_lanes = 0;
@@ -377,11 +368,19 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 r.u8_lanes = hi_lanes;
                 if (any_hi) {
                     uint4 *s = u8_slots + 5 * __popc(hi_lanes & ((1u << lane) - 1u));   // 80 contiguous bytes per slot
-                    __stcs(s + 0, make_uint4(pl[0], pl[1], pl[2], pl[3]));
-                    __stcs(s + 1, make_uint4(pl[4], pl[5], pl[6], pl[7]));
-                    __stcs(s + 2, make_uint4(ph[0], ph[1], ph[2], ph[3]));
-                    __stcs(s + 3, make_uint4(ph[4], ph[5], ph[6], ph[7]));
-                    __stcs(s + 4, make_uint4(in.prev, in.ends, 0u, 0u));
+                    if (DEFER_U8 == 2) {
+                        s[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        s[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                        s[2] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        s[3] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        s[4] = make_uint4(in.prev, in.ends, 0u, 0u);
+                    } else {
+                        __stcs(s + 0, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+                        __stcs(s + 1, make_uint4(pl[4], pl[5], pl[6], pl[7]));
+                        __stcs(s + 2, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                        __stcs(s + 3, make_uint4(ph[4], ph[5], ph[6], ph[7]));
+                        __stcs(s + 4, make_uint4(in.prev, in.ends, 0u, 0u));
+                    }
                 }
             } else if (hi_lanes) {
                 Utf8Pre32 ul, uh;
@@ -576,32 +575,6 @@ __device__ __forceinline__ void flatten_direct(uint32_t *out, uint64_t cap, uint
         rhi &= ~(0x80000000u >> b);
     }
 }
-// copy staged indexes to global memory with 16-byte stores; stage[a .. a+total) holds out[first .. first+total),
-// a chosen so that stage and out share their 16-byte phase.  Executed by `nthreads` threads with ids tid.
-__device__ __forceinline__ void copy_out(const uint32_t *stage, uint32_t a, uint32_t total, uint32_t *out, uint64_t first,
-                                         uint64_t cap, uint32_t tid, uint32_t nthreads) {
-    const int64_t gbase = (int64_t)first - (int64_t)a;  // out + gbase is 16-byte aligned; may be negative
-    const uint32_t end = a + total;
-    if (first + total <= cap) {                          // uniform: everything this call writes lies below the capacity
-        // whole 16-byte vectors
-        const uint32_t v_lo = (a + 3u) >> 2, v_hi = end >> 2;
-        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
-        uint4 *gv = reinterpret_cast<uint4 *>(out + gbase);
-        for (uint32_t v = v_lo + tid; v < v_hi; v += nthreads) gv[v] = sv[v];
-        // ragged head (entries a .. 3) and tail (entries 4*v_hi .. end-1): at most 3 entries each, threads 0..3 / 4..7
-        if (tid < 8u) {
-            const uint32_t j = tid < 4u ? tid : 4u * v_hi + (tid - 4u);
-            const bool head = tid < 4u && j >= a && j < end && j < 4u * v_lo;
-            const bool tail = tid >= 4u && j < end && j >= a && v_hi >= v_lo;
-            if (head || tail) out[gbase + (int64_t)j] = stage[j];
-        }
-    } else {
-        for (uint32_t j = a + tid; j < end; j += nthreads) {
-            const int64_t g = gbase + (int64_t)j;
-            if ((uint64_t)g < cap) out[g] = stage[j];
-        }
-    }
-}
 // inclusive warp scan; the shuffle's in-range predicate guards the add (no compare / select per step)
 __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t x) {
 #pragma unroll
@@ -619,132 +592,6 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t x) {
     return x;
 }
 __device__ __forceinline__ uint32_t out_phase(const uint32_t *out) { return (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u); }
-
-// ---------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------
-template <int WARPS>
-struct TileCfg {
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr int TILE = WARPS * 2048;                 // bytes per tile
-    // indexes staged in shared memory: up to 0.5 per byte for the small tiles, 0.25 for the big ones (denser tiles
-    // write straight to global memory); the staging area overlays the dead input tile
-    static constexpr int STAGE_CAP = WARPS >= 16 ? TILE / 4 : TILE / 2;
-    static constexpr int SMEM_BYTES = (STAGE_CAP + 4) * 4;    // >= 16 + TILE
-    static_assert(SMEM_BYTES >= 16 + TILE, "staging must cover the input tile");
-    // resident CTAs per SM we ask the register allocator to allow (2048 threads / 64 K registers per SM)
-#ifndef SJ_MIN_CTAS_W8
-#define SJ_MIN_CTAS_W8 4
-#endif
-    static constexpr int MIN_CTAS = WARPS <= 4 ? 8 : (WARPS == 8 ? SJ_MIN_CTAS_W8 : (WARPS == 16 ? 2 : 1));
-};
-
-template <int WARPS, bool UTF8>
-__global__ void __launch_bounds__(WARPS * 32, TileCfg<WARPS>::MIN_CTAS) stage1_kernel(const Stage1Params P) {
-    using Cfg = TileCfg<WARPS>;
-    constexpr int TILE = Cfg::TILE;
-    extern __shared__ __align__(128) uint8_t smem_raw[];   // [0,16) halo, [16,16+TILE) tile; later: index staging
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_wc0[WARPS], s_wc1[WARPS];   // warp counts if the warp starts outside / inside a string
-    __shared__ uint32_t s_wflags[WARPS];
-    __shared__ uint32_t s_woff[WARPS];                // rank of the warp's first index inside the tile (actual parity)
-    __shared__ uint32_t s_ws[WARPS];                  // actual "starts inside a string" of each warp
-    __shared__ uint32_t s_tail;                       // bit0 e_out, bit1 p_out of the tile
-    __shared__ uint32_t s_total, s_base;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar = smem_u32(&s_mbar);
-
-    // ---- ticket + bulk load -------------------------------------------------------------------
-    if (tid == 0) {
-        s_tile = P.tile_begin + atomicAdd(P.ticket, 1u);
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int tile = (int)s_tile;
-    const int64_t tb = (int64_t)tile * TILE;               // aligned coordinate of the tile's first byte
-    if (tid == 0) {
-        int64_t nbytes = (int64_t)P.alen - tb;
-        nbytes = nbytes > TILE ? TILE : nbytes;
-        nbytes = (nbytes + 15) & ~15ll;                     // stays inside the last 16-byte line of the data
-        const uint32_t halo = tile > 0 ? 16u : 0u;          // 16 bytes of the previous tile (carry look-behind)
-        mbar_expect_tx(bar, (uint32_t)nbytes + halo);
-        bulk_load(smem_u32(smem_raw) + 16u - halo, P.abase + tb - halo, (uint32_t)nbytes + halo, bar);
-    }
-    mbar_wait(bar, 0);
-
-    // ---- phase 1 ---------------------------------------------------------------------------------
-    LanePhase1 ph;
-    {
-        LaneInput in;
-        warp_load<UTF8>(in, smem_raw + 16, warp, lane, tile, tb, TILE, P);
-        warp_compute<UTF8>(ph, in, lane, P);
-    }
-    if (lane == 0) {
-        s_wc0[warp] = ph.wc0;
-        s_wc1[warp] = ph.wc1;
-        s_wflags[warp] = ph.wflags;
-        if (warp == WARPS - 1) s_tail = ph.tail;
-    }
-    __syncthreads();  // A: warp summaries visible; every lane has its bytes in registers (shared input is dead)
-
-    // ---- warp 0: tile aggregate, look-back, inclusive prefix, verdict --------------------------------
-    if (warp == 0) {
-        const bool have = lane < WARPS;
-        uint32_t R, off0, off1;
-        const TileAgg agg = tile_aggregate(have ? s_wflags[lane] : 0u, have ? s_wc0[lane] : 0u, have ? s_wc1[lane] : 0u,
-                                           s_tail, WARPS, lane, R, off0, off1);
-        LookbackResult lb = {0, 0, 0};
-        if (tile > 0) {
-            if (lane == 0) st_desc(P.desc + tile, desc_pack_agg(P.gen, agg));
-            lb = lookback(P.desc, P.gen, tile, lane);
-        }
-        const uint32_t s_in = lb.s_in & 1u;
-        const uint32_t total = s_in ? agg.c[1] : agg.c[0];
-        TilePrefix pre;
-        pre.s_out = s_in ^ agg.par;
-        pre.e_out = agg.e_out;
-        pre.p_out = agg.p_out;
-        pre.err = lb.err | ((s_in ? agg.un[1] : agg.un[0]) ? EF_UNESCAPED : 0u) | (agg.u8 ? EF_UTF8 : 0u);
-        pre.count = lb.base + total;
-        if (lane == 0) st_desc(P.desc + tile, desc_pack_prefix(P.gen, pre));
-        if (have) {
-            s_woff[lane] = s_in ? off1 : off0;
-            s_ws[lane] = s_in ^ R;
-        }
-        if (lane == 0) {
-            s_total = total;
-            s_base = lb.base;
-            if (tile == (int)P.tile_end - 1) {
-                if (P.progress) *P.progress = pre.count;
-                *P.ticket = 0;  // every tile of this launch has drawn its ticket by now
-            }
-            if (tile == (int)P.ntiles - 1) write_verdict(P, pre);
-        }
-    }
-    __syncthreads();  // B: parity entering every warp and the output cursor are known
-
-    // ---- flatten: bitmask -> ascending uint32 indexes ---------------------------------------------------
-    const uint32_t s_w = s_ws[warp] & 1u;   // the WARP starts inside a string? (the lane's own offset is already in m0/m1)
-    const uint64_t structural = s_w ? ph.m1 : ph.m0;
-    const uint32_t cnt = s_w ? ph.c1 : ph.c0;
-    const uint32_t incl = warp_inclusive_sum(cnt);
-    const uint32_t total = s_total, base = s_base;
-    const uint32_t my = s_woff[warp] + incl - cnt;           // rank of this lane's first index inside the tile
-    if (total <= (uint32_t)Cfg::STAGE_CAP) {
-        uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
-        // keep shared and global 16-byte phases equal (the output pointer itself may be only 4-byte aligned)
-        const uint32_t a = (base + out_phase(P.out)) & 3u;
-        flatten_to(stage + a + my, structural, ph.v0);
-        __syncthreads();  // C
-        copy_out(stage, a, total, P.out, base, P.cap, (uint32_t)tid, (uint32_t)Cfg::THREADS);
-    } else {
-        // very dense tile: write straight to global memory
-        flatten_direct(P.out, P.cap, (uint64_t)base + my, structural, ph.v0);
-    }
-}
 
 #endif  // __CUDACC__
 

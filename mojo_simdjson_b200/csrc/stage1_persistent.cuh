@@ -182,10 +182,6 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
             const uint32_t incl = warp_inclusive_sum(cnt);
             const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const uint64_t first = (uint64_t)S.base + (s_in ? S.off1[warp] : S.off0[warp]);  // the warp's first index
-#if SJ_SKIP_FLUSH
-            if (structural == 0x123456789ull) P.out[first] = wtotal;  // keep the values alive, write nothing
-            return;
-#endif
             if (wtotal <= (uint32_t)Cfg::WCAP) {
                 const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
                 flatten_to(stage + a + (incl - cnt), structural, old.v0);
@@ -225,14 +221,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
                         produce(i + 1);
                     }
                 }
-#if SJ_SKIP_COMPUTE
-                // debug: pretend every 6th byte is structural, no classification at all
-                ph.m0 = 0x0410410410410410ull ^ in.w[0]; ph.m1 = ~ph.m0; ph.c0 = (uint32_t)__popcll(ph.m0); ph.c1 = 64 - ph.c0;
-                ph.v0 = (uint32_t)in.g0; ph.wc0 = __reduce_add_sync(0xFFFFFFFFu, ph.c0); ph.wc1 = __reduce_add_sync(0xFFFFFFFFu, ph.c1);
-                ph.wflags = 0; ph.tail = 0;
-#else
                 warp_compute<UTF8>(ph, in, lane, P);
-#endif
             }
             TileSlot &S = s_slot[slot];
             uint32_t order = 0;

@@ -224,6 +224,28 @@ struct FlattenCfg {
     static constexpr int SMEM_BYTES = FW * (WCAP + 4) * 4;
 };
 
+// one warp flattens chunk c: carry word -> plane -> popcount, warp scan, extraction into `stage` (the warp's staging area
+// of WCAP + 4 entries in shared memory), 16-byte stores.  BitIndexer.write, reference json_structural_indexer.mojo:46-58.
+template <int WCAP>
+__device__ __forceinline__ void flatten_chunk(const Stage1Params &P, uint32_t c, uint64_t carry, uint64_t structural, uint32_t *stage, int lane) {
+    const uint64_t first = carry & CARRY_RANK_MASK;
+    const uint32_t lo = (uint32_t)structural, hi = (uint32_t)(structural >> 32);
+    const uint32_t cnt_lo = (uint32_t)__popc(lo), cnt = cnt_lo + (uint32_t)__popc(hi);
+    const uint32_t incl = warp_inclusive_sum(cnt);
+    const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t v0 = c * 2048u + (uint32_t)lane * 64u - P.mis;
+    if (wtotal <= (uint32_t)WCAP) {
+        const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
+        const uint32_t sp = smem_u32(stage) + 4u * (a + (incl - cnt));
+        flatten_word_pair(sp, lo, v0 + 31u);
+        flatten_word_pair(sp + 4u * cnt_lo, hi, v0 + 63u);   // (the popcount of the low word is needed for the scan anyway)
+        __syncwarp();
+        copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
+    } else {
+        flatten_direct(P.out, P.cap, first + (incl - cnt), structural, v0);
+    }
+}
+
 // chunks [chunk_begin, chunk_end): one warp each
 template <int FW>
 __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
@@ -238,23 +260,8 @@ __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatte
     const uint64_t carry = __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c));
     if (P.spec_flag && gave_up == P.gen) return;
     const uint32_t s_w = (uint32_t)(carry >> 63);
-    const uint64_t first = carry & CARRY_RANK_MASK;
     const uint64_t structural = __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)c * 64 + s_w * 32 + lane));
-    const uint32_t lo = (uint32_t)structural, hi = (uint32_t)(structural >> 32);
-    const uint32_t cnt_lo = (uint32_t)__popc(lo), cnt = cnt_lo + (uint32_t)__popc(hi);
-    const uint32_t incl = warp_inclusive_sum(cnt);
-    const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const uint32_t v0 = c * 2048u + (uint32_t)lane * 64u - P.mis;
-    if (wtotal <= (uint32_t)Cfg::WCAP) {
-        const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
-        const uint32_t sp = smem_u32(stage) + 4u * (a + (incl - cnt));
-        flatten_word_pair(sp, lo, v0 + 31u);
-        flatten_word_pair(sp + 4u * cnt_lo, hi, v0 + 63u);   // (the popcount of the low word is needed for the scan anyway)
-        __syncwarp();
-        copy_out_warp(stage, a, wtotal, P.out, first, P.cap, (uint32_t)lane);
-    } else {
-        flatten_direct(P.out, P.cap, first + (incl - cnt), structural, v0);
-    }
+    flatten_chunk<Cfg::WCAP>(P, c, carry, structural, stage, lane);
 }
 
 #endif  // __CUDACC__

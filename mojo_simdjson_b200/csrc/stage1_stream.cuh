@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
                 fetch(b);
                 if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
             }
-            warp_compute<UTF8, true>(ph, in, lane, P, P.u8_slots + (size_t)c * (8 * 5));
+            warp_compute<UTF8, 1>(ph, in, lane, P, P.u8_slots + (size_t)c * (8 * 5));
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
         __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);

@@ -44,9 +44,15 @@ class Stage1Context:
     def set_warps(self, warps: int) -> None:
         rc = self._lib.sjb200_ctx_set_warps(self._ctx, warps)
         if rc != errors.SUCCESS:
-            raise ValueError("warps must be 0, 2, 4, 8, 12, 16, 24 or 32")
+            raise ValueError("warps must be 0, 2, 4, 8, 16 or 24")
 
-    KERNELS = {"auto": 0, "tile": 1, "persistent": 2, "dataflow": 3, "split": 4, "stream": 5}
+    KERNELS = {"auto": 0, "persistent": 2, "split": 4, "stream": 5, "fused": 6}
+
+    def reserve(self, length: int, stream_pipeline: bool = False) -> None:
+        """Allocate the scratch for documents of up to `length` bytes now (otherwise: on first use, stream ordered)."""
+        rc = self._lib.sjb200_ctx_reserve(self._ctx, length, 1 if stream_pipeline else 0)
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"sjb200_ctx_reserve failed: {errors.NAMES.get(rc, rc)}")
 
     def set_kernel(self, kind) -> None:
         """Force the kernel organisation (include/simdjson_b200.h, SJB200_KERNEL_*); results do not depend on it."""

@@ -20,7 +20,7 @@ DEFAULT_MAX_LEN = 64 << 20
 class DomParserImplementation:
     """Stage-1 half of the reference's DomParserImplementation, backed by the B200 kernel."""
 
-    def __init__(self, device: int = 0, max_len: int = DEFAULT_MAX_LEN, validate_utf8: bool = False):
+    def __init__(self, device: int = 0, max_len: int = DEFAULT_MAX_LEN, validate_utf8: bool = False, chunk_bytes: int | None = None):
         self._lib = _native.lib()
         if self._lib.sjb200_device_count() <= 0:
             raise RuntimeError("no CUDA device: the stage-1 path has no CPU fallback")
@@ -38,6 +38,8 @@ class DomParserImplementation:
         rc = self._lib.sjb200_ctx_create(device, max_len, max_len, 0, C.byref(self._ctx))
         if rc != errors.SUCCESS:
             raise RuntimeError(f"sjb200_ctx_create failed: {errors.NAMES.get(rc, rc)}")
+        if chunk_bytes is not None and self._lib.sjb200_ctx_set_chunk_bytes(self._ctx, chunk_bytes) != errors.SUCCESS:
+            raise ValueError("chunk_bytes must be >= 4096")
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
@@ -71,11 +73,11 @@ class DomParserImplementation:
             buffer = np.frombuffer(bytes(buffer), dtype=np.uint8)
         buffer = np.ascontiguousarray(buffer, dtype=np.uint8)
         n_bytes = int(buffer.size)
+        if n_bytes > self._max_len:     # before allocate(): an oversize input must not cost 4 * len bytes of host memory first
+            return errors.CAPACITY
         self.allocate(n_bytes)
         self.buf = buffer
         self.length = n_bytes
-        if n_bytes > self._max_len:
-            return errors.CAPACITY
         n = C.c_uint32(self.n_structural_indexes)
         u8 = C.c_int32(0)
         rc = self._lib.sjb200_stage1(self._ctx, buffer.ctypes.data if n_bytes else None, n_bytes,

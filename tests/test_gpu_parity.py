@@ -144,15 +144,14 @@ def test_validate_utf8_flag_through_facade():
         p.close()
 
 
-def test_host_path_streams_in_chunks(monkeypatch):
+def test_host_path_streams_in_chunks():
     """sjb200_stage1 copies / indexes / copies back chunk by chunk (look-back state carried across launches)."""
     from mojo_simdjson_b200 import synth
     from mojo_simdjson_b200.dom_parser_implementation import DomParserImplementation
 
-    monkeypatch.setenv("SJB200_CHUNK_MIB", "1")
     size = (20 << 20) + 12345
     doc = synth.status_array(size)
-    p = DomParserImplementation(0, max_len=size)
+    p = DomParserImplementation(0, max_len=size, chunk_bytes=1 << 20)
     try:
         want = oracle.stage1(doc, impl="fast")
         assert p.stage1(doc) == want.error == 0
@@ -176,7 +175,7 @@ def test_host_path_streams_in_chunks(monkeypatch):
 # ------------------------------------------------------------------------------------------------
 # config 5: adversarial set, device-resident path, every tile shape, aligned and misaligned input
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("warps", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("warps", [2, 4, 8, 16, 24])
 def test_adversarial_corpus_device(dev, scratch, warps):
     tiles = tuple(sorted({warps * 2048, 4096}))
     corpus = cases.adversarial_cases(tile_bytes=tiles)
@@ -194,8 +193,8 @@ def test_adversarial_corpus_device(dev, scratch, warps):
                 raise AssertionError(f"case {name} mis={mis} warps={warps}") from e
 
 
-@pytest.mark.parametrize("kernel,warps", [("tile", 8), ("persistent", 8), ("persistent", 24), ("dataflow", 4), ("dataflow", 8),
-                                          ("dataflow", 12), ("split", 8), ("split", 16), ("stream", 8), ("stream", 2)])
+@pytest.mark.parametrize("kernel,warps", [("persistent", 2), ("persistent", 4), ("persistent", 8), ("persistent", 16), ("persistent", 24),
+                                          ("split", 8), ("split", 16), ("stream", 8), ("stream", 2), ("fused", 8), ("fused", 2)])
 def test_adversarial_corpus_every_kernel_organisation(dev, scratch, kernel, warps):
     """The same corpus through each kernel organisation (sjb200_ctx_set_kernel): results must not depend on it."""
     tiles = tuple(sorted({warps * 2048, 4096}))
@@ -220,7 +219,7 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
             head = b'["' + b"a" * (pad - 2 - run) if pad - 2 - run >= 0 else b'["'
             data = head + b"\\" * 0 + b"\\"[:1] * run + b'"x", "y\\"", 1, {"k": "\\\\"}]' + b" " * 3000 + b"[]"
             want = oracle.stage1(data, impl="ref")
-            for kernel in ("stream", "persistent"):
+            for kernel in ("stream", "fused", "persistent"):
                 res, out = run_device(dev, scratch, data, kernel=kernel, warps=8)
                 try:
                     assert_same(res, out, want)
@@ -230,14 +229,15 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
     ok = b'{"a": [1, 2, 3], "b": "' + b"z" * 9000 + b'"}'
     bad = b'["' + b"a" * 2040 + b"\\"[:1] * 200 + b'" ]'
     wok, wbad = oracle.stage1(ok), oracle.stage1(bad)
-    for _ in range(6):
-        res, out = run_device(dev, scratch, ok, kernel="stream")
-        assert_same(res, out, wok)
-        res, out = run_device(dev, scratch, bad, kernel="stream")
-        assert_same(res, out, wbad)
+    for kernel in ("stream", "fused"):
+        for _ in range(6):
+            res, out = run_device(dev, scratch, ok, kernel=kernel)
+            assert_same(res, out, wok)
+            res, out = run_device(dev, scratch, bad, kernel=kernel)
+            assert_same(res, out, wbad)
 
 
-@pytest.mark.parametrize("kernel", ["stream", "split", "persistent"])
+@pytest.mark.parametrize("kernel", ["fused", "stream", "split", "persistent"])
 def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
     """2 KiB chunks that contribute no index (inside a long string) at every 16-byte phase of the output cursor, and chunks
     that contribute 1, 2, 3 indexes: the flatten kernel's vector copy must not touch a neighbour's entries."""
@@ -266,7 +266,7 @@ def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
         assert int((scratch.out[:shift] != -1).sum()) == 0
 
 
-@pytest.mark.parametrize("kernel", ["split", "stream"])
+@pytest.mark.parametrize("kernel", ["split", "stream", "fused"])
 def test_split_pair_capacity_and_flags(dev, scratch, kernel):
     data = b'[' + b'1,' * 40000 + b'1]'
     want = oracle.stage1(data, impl="fast")
@@ -325,8 +325,11 @@ def test_capacity(dev, scratch):
 def test_dense_tile_takes_direct_path(dev, scratch):
     data = b"[" + b"1," * 100000 + b"1]"  # every byte structural: > 0.5 per byte, bypasses staging
     want = oracle.stage1(data, impl="fast")
-    for warps in (2, 8, 16, 32):
+    for warps in (2, 8, 16, 24):
         res, out = run_device(dev, scratch, data, warps=warps)
+        assert_same(res, out, want)
+    for kernel in ("fused", "stream", "split"):
+        res, out = run_device(dev, scratch, data, warps=8, kernel=kernel)
         assert_same(res, out, want)
 
 
@@ -349,12 +352,12 @@ def test_alternating_kernel_kinds_and_tile_shapes(dev, scratch):
     """Persistent launches alternate two ticket counters; launches of the other kernel in between must not disturb them."""
     a = b'{"a":"' + b"x" * 3000 + b'","b":[1,2,3]}'
     wa = oracle.stage1(a)
-    for warps in (2, 32, 2, 2, 32, 32, 2, 16, 4, 32, 8, 2, 24, 2):
+    for warps in (2, 24, 2, 2, 24, 24, 2, 16, 4, 24, 8, 2, 24, 2):
         res, out = run_device(dev, scratch, a, warps=warps)
         assert_same(res, out, wa)
-    seq = [("split", 8), ("persistent", 2), ("tile", 2), ("split", 16), ("split", 8), ("dataflow", 8), ("tile", 8), ("split", 8),
-           ("persistent", 16), ("dataflow", 4), ("dataflow", 4), ("split", 16), ("stream", 8), ("stream", 8), ("tile", 2),
-           ("stream", 2), ("persistent", 2), ("stream", 16), ("split", 8), ("stream", 4)]
+    seq = [("split", 8), ("persistent", 2), ("fused", 2), ("split", 16), ("split", 8), ("fused", 8), ("fused", 8), ("split", 8),
+           ("persistent", 16), ("fused", 4), ("stream", 4), ("split", 16), ("stream", 8), ("stream", 8), ("fused", 2),
+           ("stream", 2), ("persistent", 2), ("stream", 16), ("split", 8), ("stream", 4), ("fused", 24), ("persistent", 24)]
     for kernel, warps in seq:
         res, out = run_device(dev, scratch, a, warps=warps, kernel=kernel)
         assert_same(res, out, wa)
@@ -384,12 +387,18 @@ def test_twitter_like_631k(dev):
     assert want.error == 0
     inp = torch.from_numpy(doc).cuda()
     out = torch.empty(doc.size + 3, dtype=torch.int32, device="cuda")
-    for warps in (0, 2, 4, 8, 16, 32):
+    for warps in (0, 2, 4, 8, 16, 24):
         dev.set_warps(warps)
         out.fill_(-1)
         res = dev.index(inp, out)
         assert_same(res, out, want)
     dev.set_warps(0)
+    for kernel in ("fused", "stream", "split"):
+        dev.set_kernel(kernel)
+        out.fill_(-1)
+        res = dev.index(inp, out)
+        assert_same(res, out, want)
+    dev.set_kernel("auto")
 
 
 def test_document_64mib_full_compare(dev):
@@ -401,12 +410,14 @@ def test_document_64mib_full_compare(dev):
     assert want.error == 0
     inp = torch.from_numpy(doc).cuda()
     out = torch.empty(size // 3, dtype=torch.int32, device="cuda")
-    for warps in (2, 8, 16, 32):
+    for kernel, warps in (("persistent", 2), ("persistent", 8), ("persistent", 16), ("persistent", 24), ("split", 0), ("stream", 0), ("fused", 0), ("auto", 0)):
+        dev.set_kernel(kernel)
         dev.set_warps(warps)
         out.fill_(-1)
         res = dev.index(inp, out)
         assert_same(res, out, want)
     dev.set_warps(0)
+    dev.set_kernel("auto")
     # error injected far into the document: verdict parity at scale
     bad = doc.copy()
     bad[size - 1000] = 0x22
@@ -505,7 +516,7 @@ def test_ndjson_batch_driver_single_rank(dev):
         assert v.errors[1] == wbad.error and v.errors[0] == 0
 
 
-@pytest.mark.parametrize("kernel", ["auto", "persistent"])
+@pytest.mark.parametrize("kernel", ["auto", "stream", "persistent"])
 def test_maximum_length_document(kernel):
     """len = 2^32 - 1, the largest document the uint32 index format allows (reference include/base.mojo:2): index values
     above 2^31, chunk arithmetic at the top of the 32-bit range, trailer = len.  Built on the device, expected output
@@ -545,7 +556,7 @@ def test_maximum_length_document(kernel):
         ctx.close()
 
 
-@pytest.mark.parametrize("kernel", ["stream", "persistent"])
+@pytest.mark.parametrize("kernel", ["fused", "stream", "persistent"])
 def test_utf8_verdicts_sparse_lanes(dev, scratch, kernel):
     """Valid and invalid UTF-8 sequences in otherwise ASCII documents, placed so that they straddle lane (64 B) and chunk
     (2 KiB) boundaries, sit at the very start / end of the document, or follow a lane that is pure ASCII: in the stream

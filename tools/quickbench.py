@@ -11,7 +11,7 @@ d_in = torch.from_numpy(doc).cuda(); d_out = torch.empty(size // 3, dtype=torch.
 ctx = device.Stage1Context(0)
 for kernel in os.environ.get('KERNELS', 'persistent,split').split(','):
     ctx.set_kernel(kernel)
-    for nw in [int(x) for x in os.environ.get('NWS', '8,16').split(',')]:
+    for nw in [int(x) for x in os.environ.get('NWS', '0').split(',')]:
         ctx.set_warps(nw)
         for _ in range(5): ctx.enqueue(d_in, d_out, 0)
         torch.cuda.synchronize()
