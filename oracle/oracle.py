@@ -126,6 +126,52 @@ def stage1(data, flags: int = 0, impl: str = "ref", cap: int | None = None, nati
     return Stage1Result(err, n.value if assigned else None, count, out[:keep].copy(), int(u8.value), trailer)
 
 
+_simd = None
+
+
+def simd_lib() -> C.CDLL:
+    """liboracle_stage1_simd.so: the AVX-512 / AVX2 "cpu_simd" baseline (oracle/stage1_simd.c)."""
+    global _simd
+    if _simd is None:
+        path = os.path.join(_HERE, "liboracle_stage1_simd.so")
+        src = os.path.join(_HERE, "stage1_simd.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle_stage1_simd.so"])
+        L = C.CDLL(path)
+        L.simd_stage1_level.restype = C.c_int
+        L.simd_stage1_level.argtypes = []
+        L.simd_stage1.restype = C.c_int32
+        L.simd_stage1.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int32), C.c_uint32, C.c_int]
+        _simd = L
+    return _simd
+
+
+def simd_level() -> int:
+    """2 = AVX-512 + pclmulqdq, 1 = AVX2 + pclmulqdq, 0 = this CPU has neither."""
+    return int(simd_lib().simd_stage1_level())
+
+
+def stage1_simd(data, flags: int = 0, cap: int | None = None, level: int = 0) -> Stage1Result:
+    """The cpu_simd baseline with the oracle's result shape (tests compare it with the oracle bit for bit)."""
+    L = simd_lib()
+    a = _as_u8(data)
+    n_bytes = int(a.size)
+    if cap is None:
+        cap = n_bytes + 3 + 8
+    out = np.full(max(cap, 1), 0xDEADBEEF, dtype=np.uint32)
+    n = C.c_uint32(0xFFFFFFFF)
+    nw = C.c_uint64(0)
+    u8 = C.c_int32(0)
+    err = L.simd_stage1(a.ctypes.data if n_bytes else None, n_bytes, out.ctypes.data, cap, C.byref(n), C.byref(nw), C.byref(u8), flags, level)
+    if err < 0:
+        raise RuntimeError("this CPU has neither AVX-512 nor AVX2 with pclmulqdq")
+    assigned = n.value != 0xFFFFFFFF
+    count = int(nw.value)
+    keep = min(count + (3 if assigned else 0), cap)
+    return Stage1Result(err, n.value if assigned else None, count, out[:keep].copy(), int(u8.value), assigned)
+
+
 def utf8_valid(data, impl: str = "dfa") -> bool:
     L = lib()
     a = _as_u8(data)

@@ -191,3 +191,54 @@ def test_document_starts_side_output():
     assert bytes(sb) == b'{":[1,2]}[3]4"{":{}}'
     starts = oracle.document_starts(sb)
     assert [k for k, f in enumerate(starts) if f] == [0, 9, 12, 13, 14]   # { [ 4 " {
+
+
+# ------------------------------------------------------------------------------------------------
+# "cpu_simd" (oracle/stage1_simd.c): the AVX-512 / AVX2 + pclmulqdq baseline bench.py times beside the faithful port
+# ------------------------------------------------------------------------------------------------
+def _simd_levels():
+    try:
+        have = oracle.simd_level()
+    except Exception:
+        return []
+    return [lvl for lvl in (1, 2) if lvl <= have]
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_cpu_simd_baseline_matches_the_oracle(level):
+    if level not in _simd_levels():
+        pytest.skip("this CPU lacks the instruction set")
+    for name, data in cases.adversarial_cases():
+        for flags in (0, 1):
+            w = oracle.stage1(data, flags=flags, impl="fast" if len(data) > 20000 else "ref")
+            g = oracle.stage1_simd(data, flags=flags, level=level)
+            assert (g.error, g.n, g.n_written, g.utf8_error) == (w.error, w.n, w.n_written, w.utf8_error), (name, flags)
+            assert np.array_equal(g.indexes[: w.indexes.size], w.indexes), (name, flags)
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_cpu_simd_baseline_capacity(level):
+    if level not in _simd_levels():
+        pytest.skip("this CPU lacks the instruction set")
+    data = b"[" + b"1," * 3000 + b"1]"
+    w = oracle.stage1(data)
+    for cap in (w.n + 3, w.n + 2, 100, 3):
+        g = oracle.stage1_simd(data, cap=cap, level=level)
+        if cap >= w.n + 3:
+            assert g.error == 0 and np.array_equal(g.indexes, w.indexes)
+        else:
+            assert g.error == oracle.CAPACITY and g.n is None
+            keep = min(cap, w.n)
+            assert np.array_equal(g.indexes[:keep], w.indexes[:keep])
+
+
+def test_cpu_simd_baseline_on_the_bench_workload():
+    if not _simd_levels():
+        pytest.skip("this CPU lacks the instruction set")
+    from mojo_simdjson_b200 import synth
+
+    for doc in (synth.status_array(3 << 20), synth.ndjson(2 << 20), synth.twitter_like()):
+        w = oracle.stage1(doc, impl="fast")
+        g = oracle.stage1_simd(doc)
+        assert g.error == w.error == 0 and g.n == w.n and g.utf8_error == w.utf8_error == 0
+        assert np.array_equal(g.indexes[: w.n + 3], w.indexes)
