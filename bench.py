@@ -383,7 +383,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # which kernel organisation the library picks for this document size (capi.cu: SPLIT_MIN_BYTES) unless forced
     seg = size / nseg
-    kind = args.kernel if args.kernel != "auto" else ("fused" if seg >= (8 << 20) else "persistent")
+    kind = args.kernel if args.kernel != "auto" else ("stream" if seg >= (160 << 20) else "split" if seg >= (48 << 20) else "persistent")
     prof = ncu_traffic(kind)
     if kind == "stream":
         kname = ("stage-1 stream pipeline, 6 launches per document: stage1_stream_classify_kernel -> stage1_utf8_lanes_kernel -> "

@@ -207,6 +207,53 @@ int32_t sjb200_batch_run_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, con
                                       uint32_t first, uint32_t count, uint32_t *d_idx, const uint64_t *idx_offsets,
                                       uint64_t idx_capacity, int32_t *d_status, uint32_t flags);
 
+/*
+ * Multi-GPU batch driver: owns one context per GPU and the NCCL communicators.  The batch
+ * is cut at '\n' into one shard per GPU and every shard into segments of at most ~seg_bytes (each segment = one reference
+ * stage-1 call, dom_parser_implementation.mojo:65-69, on that byte range).  Per pass the GPUs exchange ONE NCCL all-gather
+ * of the {error, n} rows of their segments -- the only inter-GPU traffic; the worst error is the maximum over the rows.
+ * NCCL is loaded at run time (libnccl.so.2, or the path in SJB200_NCCL_LIB) and only when more than one GPU takes part.
+ *
+ * sjb200_batch_create: ONE process drives `ngpus` devices (devices == NULL: 0 .. ngpus-1; communicators from
+ *   ncclCommInitAll).  max_shard_bytes > 0 also allocates, per GPU, staging for the host-batch entry point sjb200_batch_run.
+ * sjb200_batch_create_rank: one process PER GPU (torchrun / MPI): rank `rank` of `world` on `device`; nccl_id = the 128
+ *   bytes sjb200_batch_unique_id produced on rank 0, carried to the other ranks by the caller (ncclCommInitRank inside).
+ * max_segments: rows per GPU in the exchange (<= 256).
+ */
+typedef struct sjb200_batch sjb200_batch;
+int32_t sjb200_batch_unique_id(void *id128);
+int32_t sjb200_batch_create(int32_t ngpus, const int32_t *devices, uint64_t max_shard_bytes, uint64_t seg_bytes,
+                            uint32_t max_segments, uint32_t flags, sjb200_batch **batch);
+int32_t sjb200_batch_create_rank(int32_t device, int32_t rank, int32_t world, const void *nccl_id, uint64_t max_shard_bytes,
+                                 uint64_t seg_bytes, uint32_t max_segments, uint32_t flags, sjb200_batch **batch);
+int32_t sjb200_batch_destroy(sjb200_batch *batch);
+/* GPUs this process drives, and the context of one of them (e.g. to put it on an existing stream). */
+int32_t sjb200_batch_local_gpus(sjb200_batch *batch);
+int32_t sjb200_batch_ctx(sjb200_batch *batch, int32_t local_gpu, sjb200_ctx **ctx);
+/*
+ * Host batch in, host indexes out (single-process mode): shards [0, len) over the GPUs by line ranges, copies every shard
+ * to its GPU, indexes its segments, exchanges the verdicts, copies every segment's n + 3 entries back.  On return
+ * seg_offsets[0 .. *n_segments] are the byte offsets of the segments in buf, seg_idx_offsets[s] the entry of idx_out where
+ * segment s starts (= seg_offsets[s] + 3 * s), seg_counts / seg_errors the per-segment n and verdict (may be NULL),
+ * *global_error the worst verdict over the whole batch.  CAPACITY if a shard exceeds max_shard_bytes, the batch needs more
+ * than max_total_segments segments, or idx_capacity < len + 3 * segments.
+ */
+int32_t sjb200_batch_run(sjb200_batch *batch, const uint8_t *buf, uint64_t len, uint32_t *idx_out, uint64_t idx_capacity,
+                         uint64_t *seg_offsets, uint64_t *seg_idx_offsets, uint32_t *seg_counts, int32_t *seg_errors,
+                         uint32_t max_total_segments, uint32_t *n_segments, int32_t *global_error, uint32_t flags);
+/*
+ * Device-resident shards (what the scaling benchmark times).  plan: cuts the shard that is resident on local GPU
+ * `local_gpu` into segments (device-side newline search; seg_offsets / idx_offsets: max_segments + 1 entries, may be NULL).
+ * run_resident_async: one pass -- per local GPU its segments back to back into d_idx[g] (segment s at idx_offsets[s]),
+ * then the all-gather on an internal stream, so that it runs beside the kernels of the next pass; never blocks the host.
+ * finish: waits for everything in flight; all_rows (may be NULL): int32 [world][max_segments][2] = {error, n} of every
+ * segment of every rank after the most recent pass ({-1, -1}: no such segment); *global_error: the worst of them.
+ */
+int32_t sjb200_batch_plan_resident(sjb200_batch *batch, int32_t local_gpu, const uint8_t *d_shard, uint64_t shard_len,
+                                   uint64_t *seg_offsets, uint64_t *idx_offsets, uint32_t *n_segments);
+int32_t sjb200_batch_run_resident_async(sjb200_batch *batch, uint32_t *const *d_idx, const uint64_t *idx_capacities, uint32_t flags);
+int32_t sjb200_batch_finish(sjb200_batch *batch, int32_t *all_rows, int32_t *global_error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,16 @@ SIGNATURES = {
     "sjb200_batch_split_host": (_i32, [_vp, _u64, _u64, _pu64, _u32, _pu32]),
     "sjb200_batch_run_device_async": (_i32, [_vp, _vp, _pu64, _u32, _u32, _vp, _pu64, _u64, _vp, _u32]),
     "sjb200_batch_run_device": (_i32, [_vp, _vp, _pu64, _u32, _u32, _vp, _pu64, _u64, _pu32, _pi32, _pi32, _u32]),
+    "sjb200_batch_unique_id": (_i32, [_vp]),
+    "sjb200_batch_create": (_i32, [_i32, _pi32, _u64, _u64, _u32, _u32, C.POINTER(_vp)]),
+    "sjb200_batch_create_rank": (_i32, [_i32, _i32, _i32, _vp, _u64, _u64, _u32, _u32, C.POINTER(_vp)]),
+    "sjb200_batch_destroy": (_i32, [_vp]),
+    "sjb200_batch_local_gpus": (_i32, [_vp]),
+    "sjb200_batch_ctx": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "sjb200_batch_run": (_i32, [_vp, _vp, _u64, _vp, _u64, _pu64, _pu64, _pu32, _pi32, _u32, _pu32, _pi32, _u32]),
+    "sjb200_batch_plan_resident": (_i32, [_vp, _i32, _vp, _u64, _pu64, _pu64, _pu32]),
+    "sjb200_batch_run_resident_async": (_i32, [_vp, C.POINTER(_vp), _pu64, _u32]),
+    "sjb200_batch_finish": (_i32, [_vp, _pi32, _pi32]),
 }
 
 _lib = None

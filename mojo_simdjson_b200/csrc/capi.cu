@@ -24,10 +24,12 @@ namespace {
 
 constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
-// Kernel organisation by document size (device-resident documents; tools/sizesweep.py): the persistent tile kernel for
-// small documents (all 148 SMs get a tile even at a few hundred KiB), the fused kernel (classify / scan / flatten
-// interleaved in one persistent launch) from FUSED_MIN_BYTES on.
-constexpr uint64_t FUSED_MIN_BYTES = 8ull << 20;
+// Kernel organisation by document size (device-resident documents; tools/sizesweep.py, measured): the persistent tile kernel
+// for small documents (all 148 SMs get a tile even at a few hundred KiB), the split pair from SPLIT_MIN_BYTES, the stream
+// pipeline from STREAM_MIN_BYTES.  The fused kernel (stage1_fused.cuh) is selectable but never chosen automatically: it
+// measured slower than the pipeline at every size (1 GiB: 1145 vs 1871 GB/s; 64 MiB: 872 vs 1192 GB/s for the split pair).
+constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
+constexpr uint64_t STREAM_MIN_BYTES = 160ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
@@ -334,14 +336,21 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     d.utf8 = !(flags & SJB200_FLAG_NO_UTF8);
     int kind = c->kernel_kind != SJB200_KERNEL_AUTO ? c->kernel_kind : knobs().kernel;
     const bool auto_kind = kind == SJB200_KERNEL_AUTO;
-    if (auto_kind) kind = (whole_document && !c->scratch_failed && p.alen >= FUSED_MIN_BYTES) ? SJB200_KERNEL_FUSED : SJB200_KERNEL_PERSISTENT;
+    if (auto_kind) {
+        kind = SJB200_KERNEL_PERSISTENT;
+        if (whole_document && !c->scratch_failed && p.alen >= SPLIT_MIN_BYTES) kind = p.alen >= STREAM_MIN_BYTES ? SJB200_KERNEL_STREAM : SJB200_KERNEL_SPLIT;
+    }
     if (!whole_document) kind = SJB200_KERNEL_PERSISTENT;   // ranges of a document (streaming host path): look-back across launches
     d.warps = pick_warps(c, p.alen);
     if (kind == SJB200_KERNEL_SPLIT && d.warps != 8 && d.warps != 16) {
         // the split pair exists for 8- and 16-warp tiles only: an explicit shape it does not have is an error, never a silent
         // substitution of another kernel shape
-        if (c->forced_warps || knobs().warps) return SJB200_UNEXPECTED_ERROR;
-        d.warps = p.alen >= ((uint64_t)64 << 20) ? 16 : 8;
+        if (c->forced_warps || knobs().warps) {
+            if (!auto_kind) return SJB200_UNEXPECTED_ERROR;
+            kind = SJB200_KERNEL_PERSISTENT;   // chosen automatically: the persistent kernel has every shape
+        } else {
+            d.warps = p.alen >= ((uint64_t)64 << 20) ? 16 : 8;
+        }
     }
     if (!valid_warps(d.warps)) return SJB200_UNEXPECTED_ERROR;
     const uint64_t chunks = (p.alen + 2047) / 2048;
@@ -1057,3 +1066,5 @@ int32_t sjb200_batch_run_device(sjb200_ctx *c, const uint8_t *d_buf, const uint6
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+#include "batch_driver.cuh"

@@ -34,6 +34,9 @@
 #ifndef SJ_FUSED_REG
 #define SJ_FUSED_REG 56
 #endif
+#ifndef SJ_FUSED_ABL
+#define SJ_FUSED_ABL 0     // timing ablations (results are wrong): 1 = claim but do not flatten, 2 = no fence per run, 4 = classify stores nothing
+#endif
 #ifndef SJ_FUSED_LAG
 #define SJ_FUSED_LAG 1     // flatten groups a warp may take per classify run once it has fallen behind
 #endif
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(FusedCfg<NW>::MAXREG) sta
 #pragma unroll
         for (uint32_t k = 0; k < RUN; k++) {
             if (cb + k < ce) {
-                flatten_chunk<Cfg::WCAP>(P, cb + k, carry[k], structural[k], stage, lane);
+                if (!(SJ_FUSED_ABL & 1) || structural[k] == 0x123456789ull) flatten_chunk<Cfg::WCAP>(P, cb + k, carry[k], structural[k], stage, lane);
                 __syncwarp();   // the staging area is reused by the next chunk
             }
         }
@@ -321,8 +324,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(FusedCfg<NW>::MAXREG) sta
             parked += (uint32_t)__popc(ph.u8_lanes);
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
-        __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
-        __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
+        if (!(SJ_FUSED_ABL & 4) || ph.m0 == 0x123456789ull) {
+            __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
+            __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
+        }
         if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
         if (++b == DEPTH) {
             b = 0;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(FusedCfg<NW>::MAXREG) sta
             __syncwarp();   // orders every lane's mask stores before lane 0's fence
             if (lane == 0) {
                 if (UTF8 && u8_bad) P.spec_flag[1] = P.gen;
-                __threadfence();
+                if (!(SJ_FUSED_ABL & 2)) __threadfence();
                 old = atomicAdd(P.blk_done + blk, run_len);
             }
             old = __shfl_sync(0xFFFFFFFFu, old, 0);

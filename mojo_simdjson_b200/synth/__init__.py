@@ -49,3 +49,21 @@ def status_array(size: int, seed: int = SEED_DOC, out=None) -> np.ndarray:
 def ndjson(size: int, seed: int = SEED_NDJSON, out=None) -> np.ndarray:
     """One minified status object per line, exactly `size` bytes of whole lines (config 4)."""
     return _gen("sjb200_gen_ndjson", size, seed, out)
+
+
+def plant_backslash_runs(doc: np.ndarray, every: int = 1 << 20, run: int = 33, chunk: int = 2048) -> int:
+    """Adversarial variant of a generated document (config 5): about every `every` bytes, `run` backslashes ending exactly at
+    a 2 KiB boundary -- the input for which a 32-byte look-behind cannot decide the escape state entering the next chunk.
+    The run replaces ASCII bytes that hold neither a quote nor a backslash (and is followed by a non-quote byte), so the quote
+    parity of the document and its UTF-8 validity, hence its stage-1 verdicts, are unchanged.  In place; returns the number of
+    runs planted."""
+    planted = 0
+    for pos in range(every, doc.size - 2 * chunk, every):
+        b0 = pos + (-pos) % chunk
+        for b in range(b0, min(b0 + every - chunk, doc.size - chunk), chunk):
+            region = doc[b - run - 1 : b + 1]
+            if not ((region == 0x22) | (region == 0x5C) | (region >= 0x80)).any():
+                doc[b - run : b] = 0x5C
+                planted += 1
+                break
+    return planted

@@ -645,3 +645,94 @@ def test_document_starts_side_output(dev):
     starts = dev.document_starts(sbytes, res.n)
     torch.cuda.synchronize()
     assert int(starts.sum().item()) == data.count(b"\n")
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5 at its specified sizes: the heavy adversarial set through every kernel organisation,
+# and the dense 64 MiB / 192 MiB buffers (digest + n + verdict + UTF-8 verdict against the oracle)
+# ------------------------------------------------------------------------------------------------
+def _heavy_only_cases():
+    base = {name for name, _ in cases.adversarial_cases(tile_bytes=(4096, 8192, 16384))}
+    return [(n, d) for n, d in cases.adversarial_cases(tile_bytes=(4096, 8192, 16384), heavy=True) if n not in base]
+
+
+@pytest.mark.parametrize("kernel", ["fused", "stream", "split", "persistent"])
+def test_adversarial_corpus_heavy(dev, scratch, kernel):
+    """65535 / 65536 / 2^20+1 backslash runs at every offset and the larger fuzz set (cases.adversarial_cases(heavy=True))."""
+    heavy = _heavy_only_cases()
+    assert len(heavy) > 200 and any(name.startswith("bsrun:1048577@") for name, _ in heavy)
+    for k, (name, data) in enumerate(heavy):
+        want = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+        for mis in ((0, 7) if k % 5 == 0 else (0,)):
+            res, out = run_device(dev, scratch, data, mis=mis, kernel=kernel)
+            try:
+                assert_same(res, out, want)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"case {name} mis={mis} kernel={kernel}") from e
+
+
+def test_every_kernel_and_tile_shape_pair(dev, scratch):
+    """Every (organisation, warps) pair sjb200_ctx_set_warps accepts either produces the oracle's result or is refused
+    with UNEXPECTED_ERROR -- never a silently truncated index (round-1 advisor finding)."""
+    from mojo_simdjson_b200 import synth
+
+    data = bytes(synth.status_array(300_000)) + b" " * 777
+    want = oracle.stage1(data, impl="fast")
+    for kernel in ("auto", "persistent", "split", "stream", "fused"):
+        for warps in (0, 2, 4, 8, 16, 24):
+            res, out = run_device(dev, scratch, data, warps=warps, kernel=kernel)
+            if kernel == "split" and warps in (2, 4, 24):
+                assert res.error == 24 and res.n is None, (kernel, warps)
+            else:
+                assert_same(res, out, want)
+    for bad in (1, 3, 12, 32, 64):
+        with pytest.raises(ValueError):
+            dev.set_warps(bad)
+    for bad in (1, 3, 7):
+        with pytest.raises(ValueError):
+            dev.set_kernel(bad)
+
+
+def _dense_documents(size):
+    """SURVEY.md 8(d) config 5(ii) at `size` bytes: quote-dense, escape-dense, all-CJK, all-bracket, and a document with a
+    33-byte backslash run before a chunk boundary every MiB (the input that used to cost the stream pipeline a second pass)."""
+    q = np.full(size, 0x22, dtype=np.uint8)
+    e = np.empty(size, dtype=np.uint8)
+    e[0::2] = 0x5C
+    e[1::2] = 0x22
+    e[0], e[1], e[-2], e[-1] = ord("["), ord('"'), ord('"'), ord("]")
+    cjk_unit = np.frombuffer("日本語のテキスト€😀".encode("utf-8"), dtype=np.uint8)
+    cjk = np.resize(cjk_unit, size).copy()
+    cut = (size - 2) // cjk_unit.size * cjk_unit.size
+    cjk[0], cjk[1] = ord("["), ord('"')
+    cjk[2 : 2 + cut - cjk_unit.size] = np.resize(cjk_unit, cut - cjk_unit.size)
+    cjk[2 + cut - cjk_unit.size :] = ord("a")
+    cjk[-2], cjk[-1] = ord('"'), ord("]")
+    br = np.full(size, ord("["), dtype=np.uint8)
+    from mojo_simdjson_b200 import synth
+
+    runs = synth.status_array(size).copy()
+    return {"quotes": q, "escapes": e, "cjk": cjk, "brackets": br, "runs": runs}
+
+
+@pytest.mark.parametrize("size_mib", [64, 192])
+def test_dense_buffers_at_specified_sizes(dev, size_mib):
+    size = size_mib << 20
+    docs = _dense_documents(size)
+    from mojo_simdjson_b200 import synth
+
+    assert synth.plant_backslash_runs(docs["runs"]) >= size_mib - 2
+    kernels = ("auto", "stream", "persistent") if size_mib == 64 else ("auto", "stream")
+    out = torch.empty(size + 16, dtype=torch.int32, device="cuda")
+    for name, doc in docs.items():
+        want = oracle.stage1(doc, impl="fast", cap=size + 3, flags=1)
+        inp = torch.from_numpy(doc).cuda()
+        for kernel in kernels:
+            dev.set_kernel(kernel)
+            res = dev.index(inp, out, flags=1)
+            dev.set_kernel("auto")
+            assert (res.error, res.n, res.n_written, res.utf8_error) == (want.error, want.n, want.n_written, want.utf8_error), (name, kernel)
+            keep = want.indexes.size
+            got = out[:keep].cpu().numpy().view(np.uint32)
+            assert oracle.index_digest(got) == oracle.index_digest(want.indexes), (name, kernel)
+        del inp
