@@ -51,9 +51,27 @@ def build_synth(force: bool = False) -> str:
     return SYNTH_LIB
 
 
+def build_cpp_tests(force: bool = False) -> str:
+    """tests/cpp/batch_test: the multi-GPU batch driver driven from C++ alone (links the product library, the workload
+    generator and -- as the checker -- the CPU oracle)."""
+    root = os.path.dirname(PKG)
+    src = os.path.join(root, "tests", "cpp", "batch_test.cpp")
+    out = os.path.join(root, "tests", "cpp", "batch_test")
+    oracle_dir = os.path.join(root, "oracle")
+    if force or _stale(out, [src, LIB, SYNTH_LIB]):
+        subprocess.check_call(["make", "-s", "-C", oracle_dir, "liboracle_stage1.so"])
+        nvcc = os.environ.get("NVCC", "nvcc")
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-o", out, src, f"-L{PKG}", "-lsimdjson_b200", f"-L{os.path.dirname(SYNTH_LIB)}",
+                               "-lsjb200_synth", f"-L{oracle_dir}", "-loracle_stage1",
+                               "-Xlinker", "-rpath=$ORIGIN/../../mojo_simdjson_b200", "-Xlinker", "-rpath=$ORIGIN/../../mojo_simdjson_b200/synth",
+                               "-Xlinker", "-rpath=$ORIGIN/../../oracle", "-Wno-deprecated-gpu-targets"])
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force, verbose)
     build_synth(force)
+    build_cpp_tests(force)
 
 
 if __name__ == "__main__":

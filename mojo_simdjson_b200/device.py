@@ -37,6 +37,16 @@ class Stage1Context:
         if use_torch_stream:
             self.use_stream(torch.cuda.current_stream(dev))
 
+    @classmethod
+    def borrow(cls, ctx_ptr: C.c_void_p, device: torch.device) -> "Stage1Context":
+        """Wraps a context that something else owns (the in-library batch driver's): close() leaves it alone."""
+        self = cls.__new__(cls)
+        self._lib = _native.lib()
+        self.device = device
+        self._ctx = ctx_ptr
+        self._borrowed = True
+        return self
+
     def use_stream(self, stream: torch.cuda.Stream) -> None:
         self._stream = stream
         self._lib.sjb200_ctx_set_stream(self._ctx, C.c_void_p(stream.cuda_stream))
@@ -62,7 +72,8 @@ class Stage1Context:
 
     def close(self):
         if self._ctx:
-            self._lib.sjb200_ctx_destroy(self._ctx)
+            if not getattr(self, "_borrowed", False):
+                self._lib.sjb200_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
     def __del__(self):
