@@ -49,6 +49,10 @@ struct Knobs {
     int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
     int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream|fused
     uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
+    uint32_t window_chunks = (64u << 20) / 2048u;   // SJB200_WINDOW_MIB: window of the stream pipeline (0 = the whole document)
+    int corun = 0;          // SJB200_EXPERIMENT_CORUN=1: TIMING EXPERIMENT ONLY -- flatten runs beside classify on the masks / carries the
+                            // previous pass over the same document left behind (an upper bound for any overlapped organisation)
+    int classify_ctas = 2;  // SJB200_CLASSIFY_CTAS: resident classify CTAs per SM (the flatten kernel of the previous window fills the rest)
 };
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24; }
 const Knobs &knobs() {
@@ -64,6 +68,12 @@ const Knobs &knobs() {
         }
         if (const char *e = getenv("SJB200_CHUNK_MIB"))
             if (atoi(e) > 0) v.chunk_bytes = (uint64_t)atoi(e) << 20;
+        if (const char *e = getenv("SJB200_WINDOW_MIB")) {
+            const uint64_t mib = (uint64_t)(atoi(e) > 0 ? atoi(e) : 0);
+            v.window_chunks = (uint32_t)(((mib << 20) / 2048u + SPAN_BLOCK - 1) / SPAN_BLOCK * SPAN_BLOCK);   // whole scan blocks (8 MiB)
+        }
+        if (const char *e = getenv("SJB200_CLASSIFY_CTAS")) v.classify_ctas = atoi(e);
+        if (const char *e = getenv("SJB200_EXPERIMENT_CORUN")) v.corun = atoi(e);
         return v;
     }();
     return k;
@@ -101,13 +111,13 @@ struct sjb200_ctx {
     uint32_t *d_chunk_sum = nullptr;       // 16-byte chunk summaries
     uint32_t *d_block_sum = nullptr;       // stream pipeline: the same per 4096 chunks
     uint32_t *d_blk_state = nullptr;       // fused kernel: blk_done[], blk_ready[] and its own look-back descriptors
-    uint4 *d_u8_slots = nullptr;           // stream pipeline: parked bit planes of lanes whose UTF-8 validation is deferred
     uint64_t scratch_chunks = 0;
-    bool scratch_u8 = false;               // d_u8_slots covers scratch_chunks as well (only the stream pipeline needs it)
     bool scratch_failed = false;           // an allocation failed once: automatic choice stays with the persistent kernel
     uint32_t *d_spec_flag = nullptr;       // [0] speculation failed, [1] deferred UTF-8 violation (generation valued)
     cudaStream_t aux_stream = nullptr;     // stream pipeline: the deferred UTF-8 lanes are validated here, beside the scan
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    static constexpr int MAX_WINDOWS = 64;
+    cudaEvent_t win_ev[MAX_WINDOWS] = {};  // stream pipeline: classify of window w is done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -157,6 +167,11 @@ constexpr int STREAM_NW = SJ_STREAM_NW;
 constexpr int FUSED_NW = SJ_FUSED_NW;
 cudaError_t prepare_stream(int *occ) {
     using Cfg = StreamCfg<STREAM_NW>;
+    // every kernel of the pipeline asks for the same shared-memory carve-out: kernels with different L1 / shared splits
+    // cannot share an SM, and scan + flatten of one window must run beside the classify CTAs of the next
+    cudaFuncSetAttribute(stage1_span_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_span_carries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
 cudaError_t prepare_fused(int *occ) {
@@ -201,35 +216,62 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
     return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
 }
+// The stream pipeline (stage1_stream.cuh): per window classify on `s`; scan + flatten of the window on the context's second
+// stream behind it, i.e. beside the classify launch of the next window.  `s` finally waits for the second stream.
 template <bool UTF8>
 cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = StreamCfg<STREAM_NW>;
+    constexpr int FW = SJ_K3_FW;
+    const Knobs &k = knobs();
+    const bool pdl = k.pdl != 0;
     const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
-    const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
-    const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
-    stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
-    cudaError_t e = cudaGetLastError();
-    const bool pdl = knobs().pdl != 0;
-    if (e == cudaSuccess && UTF8) {
-        // The lanes whose UTF-8 validation the classify kernel deferred: on the context's second stream, beside the two
-        // (latency-bound) scan launches and the start of the flatten kernel.  Nothing on `s` needs its result before the
-        // last launch of the document, which folds a violation into the verdict (stage1_persistent.cuh).
-        const unsigned u8_ctas = (nchunks * U8_SLOTS + 255) / 256;
-        e = cudaEventRecord(c->ev_fork, s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
+    uint32_t win = k.window_chunks ? k.window_chunks : nchunks;                 // chunks per window, a multiple of SPAN_BLOCK
+    if ((nchunks + win - 1) / win > (uint32_t)sjb200_ctx::MAX_WINDOWS) win = (((nchunks + sjb200_ctx::MAX_WINDOWS - 1) / sjb200_ctx::MAX_WINDOWS + SPAN_BLOCK - 1) / SPAN_BLOCK) * SPAN_BLOCK;
+    const uint32_t nwin = (nchunks + win - 1) / win;
+    const bool two_streams = nwin > 1;
+    cudaStream_t s2 = two_streams ? c->aux_stream : s;
+    cudaError_t e = cudaSuccess;
+    if (k.corun) {   // timing experiment (see Knobs::corun): classify + scans on s, flatten of the whole document on the second stream at once
+        e = cudaEventRecord(c->win_ev[0], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, c->win_ev[0], 0);
+        const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
+        const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
         if (e == cudaSuccess) {
-            stage1_utf8_lanes_kernel<<<u8_ctas, 256, 0, c->aux_stream>>>(p, nchunks);
+            stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, 0u, nchunks);
             e = cudaGetLastError();
         }
+        if (e == cudaSuccess) e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, c->aux_stream, false, p, 0u, nchunks);
+        const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
+        if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
+        if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_join, c->aux_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_join, 0);
+        c->launches += 4;
+        return e;
     }
-    const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
-    if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
-    if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
-    constexpr int FW = SJ_K3_FW;
-    if (e == cudaSuccess)
-        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
-    if (e == cudaSuccess && UTF8) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch
+    for (uint32_t w = 0; w < nwin && e == cudaSuccess; w++) {
+        const uint32_t cb = w * win, ce = cb + win < nchunks ? cb + win : nchunks;
+        const unsigned want = (ce - cb + STREAM_NW - 1) / STREAM_NW;
+        const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
+        stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, cb, ce);
+        e = cudaGetLastError();
+        if (e == cudaSuccess && two_streams) {
+            e = cudaEventRecord(c->win_ev[w], s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, c->win_ev[w], 0);
+        }
+        const unsigned b0 = cb / SPAN_BLOCK, nblocks = (ce - cb + SPAN_BLOCK - 1) / SPAN_BLOCK;
+        // the first launch behind an event wait is an ordinary one; the two after it overlap their launch latency with their
+        // predecessor (programmatic dependent launch)
+        if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s2, pdl && !two_streams, p, nchunks, b0);
+        if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s2, pdl, p, nchunks, b0);
+        if (e == cudaSuccess)
+            e = launch_dependent(stage1_flatten_kernel<FW>, (ce - cb + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s2, pdl, p, cb, ce);
+    }
+    if (e == cudaSuccess && two_streams) {
+        e = cudaEventRecord(c->ev_join, s2);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch (and the next document)
+    }
+    c->launches += 4ull * nwin;
     return e;
 }
 template <bool UTF8>
@@ -269,25 +311,21 @@ void free_scratch(sjb200_ctx *c, cudaStream_t s) {
     if (c->d_chunk_sum) cudaFreeAsync(c->d_chunk_sum, s);
     if (c->d_block_sum) cudaFreeAsync(c->d_block_sum, s);
     if (c->d_blk_state) cudaFreeAsync(c->d_blk_state, s);
-    if (c->d_u8_slots) cudaFreeAsync(c->d_u8_slots, s);
     c->d_masks = c->d_carry = nullptr;
     c->d_chunk_sum = c->d_block_sum = c->d_blk_state = nullptr;
-    c->d_u8_slots = nullptr;
     c->scratch_chunks = 0;
-    c->scratch_u8 = false;
 }
 
 // Scratch for documents of up to `chunks` 2 KiB chunks (0.26 bytes per input byte: mask planes len/4, summaries and carry
 // words; the stream pipeline's parked UTF-8 lanes add 0.31 bytes per input byte and are allocated only when it is used).
 // Grows geometrically; allocation and release are stream ordered (cudaMallocAsync), so an enqueue never synchronises.
-cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, bool need_u8, cudaStream_t s) {
-    if (chunks <= c->scratch_chunks && (!need_u8 || c->scratch_u8)) return cudaSuccess;
+cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, cudaStream_t s) {
+    if (chunks <= c->scratch_chunks) return cudaSuccess;
     uint64_t n = chunks + 64;
     if (n < c->scratch_chunks) n = c->scratch_chunks;
     if (chunks > c->scratch_chunks && n < c->scratch_chunks * 3 / 2) n = c->scratch_chunks * 3 / 2;
     const uint64_t max_chunks = (c->max_len + 16) / 2048 + 64;
     if (n > max_chunks) n = max_chunks > chunks + 64 ? max_chunks : chunks + 64;
-    const bool u8 = need_u8 || c->scratch_u8;
     free_scratch(c, s);
     const uint64_t nblk = n / BLOCK_CHUNKS + 2;
     cudaError_t e = cudaMallocAsync(&c->d_masks, n * 512, s);
@@ -296,14 +334,12 @@ cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, bool need_u8, cudaStr
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_blk_state, nblk * 16, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_blk_state, 0, nblk * 16, s);
-    if (e == cudaSuccess && u8) e = cudaMallocAsync(&c->d_u8_slots, n * (size_t)(U8_SLOTS * U8_SLOT_VECTORS * 16), s);
     if (e != cudaSuccess) {
         free_scratch(c, s);
         cudaGetLastError();
         return e;
     }
     c->scratch_chunks = n;
-    c->scratch_u8 = u8;
     return cudaSuccess;
 }
 
@@ -355,7 +391,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     if (!valid_warps(d.warps)) return SJB200_UNEXPECTED_ERROR;
     const uint64_t chunks = (p.alen + 2047) / 2048;
     if (kind != SJB200_KERNEL_PERSISTENT) {
-        const cudaError_t e = ensure_scratch(c, chunks + 32, kind == SJB200_KERNEL_STREAM && d.utf8, c->stream);
+        const cudaError_t e = ensure_scratch(c, chunks + 32, c->stream);
         if (e != cudaSuccess) {
             if (!auto_kind) return SJB200_MEMALLOC;   // the caller asked for this organisation explicitly
             c->scratch_failed = true;                 // chosen automatically: the persistent kernel needs no scratch
@@ -375,7 +411,6 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
         p.carry = c->d_carry;
         p.chunk_sum = c->d_chunk_sum;
         p.block_sum = c->d_block_sum;
-        p.u8_slots = c->d_u8_slots;
         const uint64_t nblk = c->scratch_chunks / BLOCK_CHUNKS + 2;
         p.blk_done = c->d_blk_state;
         p.blk_ready = c->d_blk_state + nblk;
@@ -410,8 +445,9 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     const bool speculating = (d.kind == SJB200_KERNEL_STREAM || d.kind == SJB200_KERNEL_FUSED) && whole;
     if (speculating) {
         if (d.kind == SJB200_KERNEL_STREAM) {
-            e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(c, p, stream, c->sm_count * c->stream_occ);
-            c->launches += utf8 ? 5 : 4;
+            int per_sm = c->stream_occ;
+            if (knobs().classify_ctas > 0 && knobs().classify_ctas < per_sm) per_sm = knobs().classify_ctas;
+            e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * per_sm) : launch_stream<false>(c, p, stream, c->sm_count * per_sm);
         } else {
             Stage1Params pf = p;
             pf.desc = d.fdesc;
@@ -689,7 +725,7 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = cudaMalloc(&c->d_spec_flag, 256);
     if (e == cudaSuccess) e = cudaMemset(c->d_spec_flag, 0, 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int w = 0; w < sjb200_ctx::MAX_WINDOWS && e == cudaSuccess; w++) e = cudaEventCreateWithFlags(&c->win_ev[w], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -724,7 +760,8 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
         if (c->chunk_ev[k]) cudaEventDestroy(c->chunk_ev[k]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int w = 0; w < sjb200_ctx::MAX_WINDOWS; w++)
+        if (c->win_ev[w]) cudaEventDestroy(c->win_ev[w]);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -762,8 +799,8 @@ int32_t sjb200_ctx_reserve(sjb200_ctx *c, uint64_t len, uint32_t flags) {
     if (!c) return SJB200_UNINITIALIZED;
     if (len > 0xFFFFFFFFull || len > c->max_len) return SJB200_CAPACITY;
     CK(cudaSetDevice(c->device));
-    const bool u8 = (flags & 1u) != 0;   // bit 0: also the stream pipeline's parked UTF-8 lanes
-    const cudaError_t e = ensure_scratch(c, (len + 15 + 2047) / 2048 + 32, u8, c->stream);
+    (void)flags;                         // (bit 0 once asked for the global UTF-8 parking area; the lanes are parked in shared memory now)
+    const cudaError_t e = ensure_scratch(c, (len + 15 + 2047) / 2048 + 32, c->stream);
     if (e != cudaSuccess) return SJB200_MEMALLOC;
     c->scratch_failed = false;
     return SJB200_SUCCESS;

@@ -171,26 +171,55 @@ struct Utf8Pre32 {
     uint32_t p5, p4;
 };
 
-// the JSON classes of 32 bytes (reference json_character_block.mojo / haswell.mojo:44-69, as nibble conditions on planes)
+// Any function of three words in ONE LOP3.  LUT = the function evaluated on the constants TA, TB, TC (the usual truth-table
+// encoding); the host version evaluates the same table, so the emulator checks exactly what the kernel computes.
+static const uint32_t TA = 0xF0u, TB = 0xCCu, TC = 0xAAu;
+template <uint32_t LUT>
+SJ_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT & 0xFFu));
+    return d;
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < 8; i++)
+        if ((LUT >> i) & 1u) r |= ((i & 4u) ? a : ~a) & ((i & 2u) ? b : ~b) & ((i & 1u) ? c : ~c);
+    return r;
+#endif
+}
+
+// the JSON classes of 32 bytes (reference json_character_block.mojo / haswell.mojo:44-69) as 19 three-input functions of the
+// planes (a plain nibble-by-nibble formulation costs 28):
+//   op  : (b | 0x20) == table[b & 15], i.e. low nibble C with high nibble 0|2, A with 1|3, B or D with 5|7 (this includes the
+//         reference's 0x0C / 0x1A artefacts).  In all four low nibbles p3 = 1 and p2 != p1; then p0 = 0 pairs with p6 = 0 and
+//         p2 != p4 (C: p2 = 1, p4 = 0; A: p2 = 0, p4 = 1), p0 = 1 pairs with p6 = p4 = 1.
+//   ws  : 0x20 | 0x09 0x0A 0x0D: high nibble 0|2 with p4 = 0, p3 != p5, and the low three bits 000 (p5 = 1) or one of
+//         001 010 101 (p5 = 0), which is (p1 != p0) and not (p2 and p1).
 SJ_HD void classify_json32(const uint32_t p[8], Classes32 &c) {
     const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4], p5 = p[5], p6 = p[6], p7 = p[7];
-    const uint32_t u = ~p7 & ~p6;         // 00xx xxxx
-    const uint32_t v = ~p7 & p6;          // 01xx xxxx
-    const uint32_t h0 = u & ~p5 & ~p4;    // high nibble 0
-    const uint32_t h2 = u & p5 & ~p4;     // high nibble 2
-    const uint32_t h5 = v & ~p5 & p4;     // high nibble 5
-    const uint32_t k1 = u & ~p4;          // high nibble 0 or 2
-    const uint32_t k2 = u & p4;           // high nibble 1 or 3
-    const uint32_t k3 = v & p4;           // high nibble 5 or 7
-    const uint32_t a = p3 & ~p2, b = p3 & p2, cc = ~p3 & ~p2;
-    const uint32_t loA = a & p1 & ~p0, loB = a & p1 & p0, lo9 = a & ~p1 & p0;
-    const uint32_t loC = b & ~p1 & ~p0, loD = b & ~p1 & p0;
-    const uint32_t lo0 = cc & ~p1 & ~p0, lo2 = cc & p1 & ~p0;
-    c.ws = (h0 & (lo9 | loA | loD)) | (h2 & lo0);
-    c.rq = h2 & lo2;
-    c.bs = h5 & loC;
-    c.op = (k1 & loC) | (k2 & loA) | (k3 & (loB | loD));
-    c.ctl = u & ~p5;
+    c.ctl = lop3<(~TA & ~TB & ~TC)>(p7, p6, p5);                              // 000x xxxx
+    const uint32_t w2 = lop3<(~TA & ~TB & ~TC)>(p7, p6, p4);                  // high nibble 0 or 2
+    // op
+    const uint32_t a1 = lop3<((TA ^ TB) & TC)>(p2, p1, p3);
+    const uint32_t b1 = lop3<(TA & TB & TC)>(p0, p6, p4);
+    const uint32_t b2 = lop3<((TA ^ TB) & ~TC)>(p2, p4, p0);
+    const uint32_t b3 = lop3<((TA & ~TB) | TC)>(b2, p6, b1);
+    c.op = lop3<(TA & ~TB & TC)>(a1, p7, b3);
+    // whitespace
+    const uint32_t w1 = lop3<((TB ^ TC) & ~(TA & TB))>(p2, p1, p0);          // low three bits 001 010 101
+    const uint32_t z = lop3<(~TA & ~TB & ~TC)>(p2, p1, p0);                   // low three bits 000
+    const uint32_t y = lop3<((TA & TB) | (~TA & TC))>(p5, z, w1);
+    const uint32_t t = lop3<((TA ^ TB) & TC)>(p3, p5, y);
+    c.ws = w2 & t;
+    // '"' = 0010 0010
+    const uint32_t q1 = lop3<(~TA & TB & ~TC)>(p2, p1, p0);
+    const uint32_t q2 = lop3<(TA & ~TB & TC)>(p5, p3, q1);
+    c.rq = w2 & q2;
+    // '\\' = 0101 1100
+    const uint32_t x = lop3<(TA & TB & ~TC)>(p6, p4, p0);
+    const uint32_t yb = lop3<(~TA & ~TB & ~TC)>(p7, p5, p1);
+    const uint32_t l2 = lop3<(TA & TB & TC)>(p3, p2, x);
+    c.bs = l2 & yb;
 }
 // the UTF-8 lead / continuation classes of the same 32 bytes; only needed when some byte is >= 0x80
 SJ_HD void utf8_pre32(const uint32_t p[8], Utf8Pre32 &u8) {

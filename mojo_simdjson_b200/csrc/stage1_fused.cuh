@@ -46,7 +46,6 @@ namespace sjb200 {
 #if defined(__CUDACC__)
 
 constexpr uint32_t BLOCK_CHUNKS = 64;        // chunks per look-back block (128 KiB of input; counts fit the 18-bit descriptor fields)
-constexpr uint32_t WALK_MAX = 64u << 10;     // longest backslash run resolved by walking back through global memory
 
 template <int NW>
 struct FusedCfg {
@@ -70,53 +69,10 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ld_cg_u4(const void *p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint64_t ld_cg_u64(const void *p) {
     uint64_t v;
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-
-// Length of the backslash run that ends just before aligned coordinate `end` (a multiple of 16), walking back through
-// global memory 512 bytes per step; bytes before the document start (coordinate < mis) end the run.  `skip` = 1: the byte
-// at end-1 is not part of the question (it is the quote whose escapedness is asked) and the run ends at end-2.
-// Returns false if the run is longer than max_bytes.
-__device__ __forceinline__ bool backslash_run_global(const uint8_t *abase, uint64_t end, uint32_t mis, uint32_t skip, int lane,
-                                                     uint32_t max_bytes, uint32_t &run_out) {
-    uint32_t run = 0;
-    for (uint32_t step = 0; step * 512u < max_bytes + 512u; step++) {
-        const int64_t pos = (int64_t)end - 512ll * step - 16ll * (lane + 1);   // lane 0 holds the 16 bytes nearest to `end`
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (pos >= 0) {
-            const uint4 v = ld_cg_u4(abase + pos);
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        }
-        // t = number of consecutive backslashes counted from byte 15 downwards
-        uint32_t t = 0;
-        bool open = true;
-#pragma unroll
-        for (int k = 15; k >= 0; k--) {
-            uint32_t b = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            if (skip && step == 0 && lane == 0 && k == 15) b = 0x5Cu;
-            if (pos + k < (int64_t)mis) b = 0u;
-            open = open && (b == 0x5Cu);
-            t += open ? 1u : 0u;
-        }
-        const uint32_t brk = __ballot_sync(0xFFFFFFFFu, t != 16u);
-        if (brk) {
-            const int first = __ffs((int)brk) - 1;
-            run += 16u * (uint32_t)first + __shfl_sync(0xFFFFFFFFu, t, first);
-            run_out = run - skip;
-            return true;
-        }
-        run += 512u;
-    }
-    run_out = 0;
-    return false;
 }
 
 template <int NW, bool UTF8>
@@ -309,17 +265,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(FusedCfg<NW>::MAXREG) sta
             chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, unresolved);
             __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
             if (lane == 0) fetch(b);
-            if (unresolved) {   // warp-uniform, rare: a backslash run covers the whole 32-byte look-behind
-                uint32_t run;
-                if (unresolved & 1u) {
-                    if (backslash_run_global(P.abase, (uint64_t)c * 2048u, P.mis, 0u, lane, WALK_MAX, run)) in.wst.e = run & 1u;
-                    else if (lane == 0) *P.spec_flag = P.gen;
-                }
-                if (unresolved & 2u) {
-                    if (backslash_run_global(P.abase, (uint64_t)c * 2048u, P.mis, 1u, lane, WALK_MAX, run)) in.wst.p = run & 1u;
-                    else if (lane == 0) *P.spec_flag = P.gen;
-                }
-            }
+            if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0) *P.spec_flag = P.gen;   // rare, warp-uniform
             warp_compute<UTF8, 2>(ph, in, lane, P, reinterpret_cast<uint4 *>(scratch) + 5 * parked);
             parked += (uint32_t)__popc(ph.u8_lanes);
         }
@@ -337,21 +283,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(FusedCfg<NW>::MAXREG) sta
             // ---- end of a run: validate the parked lanes, signal the block, then take a turn at flattening ----
             if (UTF8 && parked) {
                 __syncwarp();
-                bool bad = false;
-                if ((uint32_t)lane < parked) {
-                    const uint4 *s = reinterpret_cast<const uint4 *>(scratch) + 5 * lane;
-                    const uint4 a = s[0], bb = s[1], d = s[2], e = s[3], f = s[4];
-                    const uint32_t pl[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
-                    const uint32_t phh[8] = {d.x, d.y, d.z, d.w, e.x, e.y, e.z, e.w};
-                    Utf8Pre32 ul, uh;
-                    utf8_pre32(pl, ul);
-                    utf8_pre32(phh, uh);
-                    const Utf8Carry uc = utf8_carry_from_prev_word(f.x);
-                    uint32_t tail_must;
-                    const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
-                    bad = (ue != 0) || (f.y != 0 && tail_must != 0);
-                }
-                if (__any_sync(0xFFFFFFFFu, bad)) u8_bad = true;
+                if (validate_parked_lanes(scratch, parked, lane)) u8_bad = true;
                 parked = 0;
                 __syncwarp();
             }

@@ -1,37 +1,49 @@
-// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of five stream-ordered launches with no
-// waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them):
+// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of stream-ordered launches with no
+// waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them).
+// The document is cut into WINDOWS (64 MiB by default); for every window, in this order:
 //
 //   stream_classify : every warp is its own pipeline.  A warp draws runs of 4 consecutive 2 KiB chunks from an atomic
 //                     counter, each chunk fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
 //                     mbarrier each) together with the 32 bytes before it, which decide the escape / scalar carries
 //                     entering the chunk.  Output per chunk: the two structural mask planes (string state entering the
-//                     chunk unknown -> one plane per parity), a 16-byte summary {count0, count1, flags, deferred lanes}
-//                     and, for at most 8 lanes with bytes >= 0x80, their parked bit planes.
-//   utf8_lanes      : UTF-8 validation of the parked lanes, one thread per lane (instead of one warp per lane).
+//                     chunk unknown -> one plane per parity) and a 16-byte summary {count0, count1, flags}.  At most 8
+//                     lanes per chunk with bytes >= 0x80 park their bit planes in the warp's shared-memory slots and are
+//                     validated 32 at a time at the end of the run (instead of one warp per lane).
 //   span_reduce     : 4096 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
-//   span_carries    : block prefix from the block aggregates, then the same local scan -> one carry word per chunk
-//                     (bit 63 = starts inside a string, bits 0..39 = rank of its first index) and the verdict.
+//   span_carries    : block prefix from the block aggregates of this and all earlier windows, then the same local scan ->
+//                     one carry word per chunk (bit 63 = starts inside a string, bits 0..39 = rank of its first index);
+//                     the last window writes the verdict.
 //   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
 //
-// The only carries stage 1 cannot resolve from a bounded look-behind are the escape state after a backslash run that
-// covers the whole 32-byte look-behind of a chunk and the scalar state after a quote preceded by 31 backslashes.  A chunk
-// that sees either raises `spec_flag` (stores the document generation); the later launches then do nothing and the
-// persistent kernel, enqueued behind them with Stage1Params::spec_flag set, redoes the document exactly.  Otherwise that
-// kernel returns at once.  Results are identical either way.
-// Reference: json_structural_indexer.mojo:83-186 (step / next / finish), restated in oracle/stage1_oracle.c.
+// The classify launches of consecutive windows follow each other on the context's stream; scan + flatten of window w run on
+// a second stream behind classify(w), i.e. BESIDE classify(w+1): the classify kernel is bound by the ALU pipe and is
+// launched at half occupancy, the flatten kernel is bound by shared memory / XU / issue slots and fills the other half of
+// every SM.  A window's mask planes (16 MiB) are written and read back inside the 126 MB L2.
+//
 #pragma once
 #include "stage1_split.cuh"
 
 #ifndef SJ_STREAMREG
-#define SJ_STREAMREG 56
+#define SJ_STREAMREG 64
 #endif
 #ifndef SJ_STREAM_DEPTH
 #define SJ_STREAM_DEPTH 3
+#endif
+#ifndef SJ_MASK_STORE
+#define SJ_MASK_STORE 0   // 0: write-back stores (the planes stay in L2 for the flatten kernel of the same window), 1: streaming stores
 #endif
 
 namespace sjb200 {
 
 #if defined(__CUDACC__)
+
+__device__ __forceinline__ void st_mask(uint64_t *p, uint64_t v) {
+#if SJ_MASK_STORE
+    __stcs(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+#else
+    *p = v;
+#endif
+}
 
 template <int NW>
 struct StreamCfg {
@@ -39,7 +51,9 @@ struct StreamCfg {
     static constexpr int DEPTH = SJ_STREAM_DEPTH;
     static constexpr int HALO = 32;
     static constexpr int BUF = 2048 + HALO;                 // 16-byte multiple
-    static constexpr int SMEM_BYTES = NW * DEPTH * BUF;
+    static constexpr int PARK = 32 * 80;                    // 32 parked UTF-8 lanes of 80 B per warp (a run of 4 chunks parks <= 8 each)
+    static constexpr int WARP_BYTES = DEPTH * BUF + PARK;
+    static constexpr int SMEM_BYTES = NW * WARP_BYTES;
     static constexpr int MAXREG = SJ_STREAMREG;
 };
 
@@ -78,6 +92,75 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
     in.wst = st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Long backslash runs.  The escape state entering a chunk (and the "previous byte is a non-quote scalar" state after a
+// quote) follows from the parity of the backslash run that ends at the chunk boundary.  32 bytes of look-behind decide
+// it unless the run fills them; then the warp walks back through global memory, 512 bytes per step (the bytes were
+// just read by a neighbouring warp: L2 hits), up to WALK_MAX bytes.  Only a longer run -- kilobytes of nothing but
+// backslashes -- raises spec_flag and costs the document a second, exact pass (stage1_persistent.cuh).
+// Reference: the carry `next_is_escaped` of json_escape_scanner.mojo:13,31, resolved without a serial dependency.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t WALK_MAX = 64u << 10;
+__device__ __forceinline__ uint4 ld_cg_u4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// Length of the backslash run that ends just before aligned coordinate `end` (a multiple of 16), walking back through
+// global memory 512 bytes per step; bytes before the document start (coordinate < mis) end the run.  `skip` = 1: the byte
+// at end-1 is not part of the question (it is the quote whose escapedness is asked) and the run ends at end-2.
+// Returns false if the run is longer than max_bytes.
+__device__ __forceinline__ bool backslash_run_global(const uint8_t *abase, uint64_t end, uint32_t mis, uint32_t skip, int lane,
+                                                     uint32_t max_bytes, uint32_t &run_out) {
+    uint32_t run = 0;
+    for (uint32_t step = 0; step * 512u < max_bytes + 512u; step++) {
+        const int64_t pos = (int64_t)end - 512ll * step - 16ll * (lane + 1);   // lane 0 holds the 16 bytes nearest to `end`
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (pos >= 0) {
+            const uint4 v = ld_cg_u4(abase + pos);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
+        // t = number of consecutive backslashes counted from byte 15 downwards
+        uint32_t t = 0;
+        bool open = true;
+#pragma unroll
+        for (int k = 15; k >= 0; k--) {
+            uint32_t b = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            if (skip && step == 0 && lane == 0 && k == 15) b = 0x5Cu;
+            if (pos + k < (int64_t)mis) b = 0u;
+            open = open && (b == 0x5Cu);
+            t += open ? 1u : 0u;
+        }
+        const uint32_t brk = __ballot_sync(0xFFFFFFFFu, t != 16u);
+        if (brk) {
+            const int first = __ffs((int)brk) - 1;
+            run += 16u * (uint32_t)first + __shfl_sync(0xFFFFFFFFu, t, first);
+            run_out = run - skip;
+            return true;
+        }
+        run += 512u;
+    }
+    run_out = 0;
+    return false;
+}
+
+
+// Resolves the carries chunk_load left open (`unresolved`, warp-uniform).  Returns false if a run exceeds WALK_MAX: the
+// caller raises spec_flag.  Once the flag is up the document is going to be redone anyway: no further walks.
+__device__ __forceinline__ bool resolve_long_runs(const Stage1Params &P, uint32_t c, uint32_t unresolved, int lane, PrevState &wst) {
+    if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return true;
+    uint32_t run;
+    if (unresolved & 1u) {
+        if (!backslash_run_global(P.abase, (uint64_t)c * 2048u, P.mis, 0u, lane, WALK_MAX, run)) return false;
+        wst.e = run & 1u;
+    }
+    if (unresolved & 2u) {
+        if (!backslash_run_global(P.abase, (uint64_t)c * 2048u, P.mis, 1u, lane, WALK_MAX, run)) return false;
+        wst.p = run & 1u;
+    }
+    return true;
+}
+
 // Chunks are handed out dynamically, TICKET_CHUNKS consecutive chunks per draw from P.ticket[3] (zero at launch; the scan
 // kernel that follows resets it).  A static partition would be slightly cheaper but assumes that every CTA of the grid is
 // resident from the start: with another kernel on the device (the NCCL verdict exchange of the previous pass, a second
@@ -88,19 +171,45 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
 constexpr uint32_t TICKET_CHUNKS = SJ_TICKET_CHUNKS;
 constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
 
+// validates the `parked` lanes a warp left in its shared-memory slots (80 B each: 16 bit-plane words, the 4 bytes before the
+// lane, its end-of-document bit), one thread per lane: the same lead / continuation / range algebra as the inline path,
+// now with every lane of the warp doing useful work
+__device__ __forceinline__ bool validate_parked_lanes(const uint8_t *park, uint32_t parked, int lane) {
+    bool bad = false;
+    if ((uint32_t)lane < parked) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(park) + 5 * lane;
+        const uint4 a = s[0], bb = s[1], d = s[2], e = s[3], f = s[4];
+        const uint32_t pl[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
+        const uint32_t ph[8] = {d.x, d.y, d.z, d.w, e.x, e.y, e.z, e.w};
+        Utf8Pre32 ul, uh;
+        utf8_pre32(pl, ul);
+        utf8_pre32(ph, uh);
+        const Utf8Carry uc = utf8_carry_from_prev_word(f.x);
+        uint32_t tail_must;
+        const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
+        bad = (ue != 0) || (f.y != 0 && tail_must != 0);
+    }
+    return __any_sync(0xFFFFFFFFu, bad);
+}
+
+// chunks [chunk_begin, chunk_end) of the document (a window of the pipeline; chunk_begin is a multiple of TICKET_CHUNKS)
 template <int NW, bool UTF8>
-__global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks) {
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks,
+                                                                                                            uint32_t chunk_begin, uint32_t chunk_end) {
     using Cfg = StreamCfg<NW>;
     constexpr int DEPTH = Cfg::DEPTH;
+    static_assert(TICKET_CHUNKS * SJ_U8_DEFER_MAX <= 32, "a run must not park more lanes than the warp's slots hold");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
     __shared__ uint32_t s_chunk[NW * DEPTH];                  // chunk held by each buffer, NO_CHUNK = nothing more to do
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t buf0 = smem_u32(smem_raw) + warp * (DEPTH * Cfg::BUF);   // shared-space addresses: 32-bit arithmetic only
-    const uint8_t *bufs = smem_raw + warp * (DEPTH * Cfg::BUF);
+    uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
+    const uint32_t buf0 = smem_u32(wbase);                    // shared-space addresses: 32-bit arithmetic only
+    const uint8_t *bufs = wbase;
+    uint8_t *park = wbase + DEPTH * Cfg::BUF;                 // parked UTF-8 lanes of the current run
     const uint32_t bar0 = smem_u32(&s_bar[warp * DEPTH]);
     volatile uint32_t *my_chunk = s_chunk + warp * DEPTH;
-    uint32_t *ticket = P.ticket + 3;
+    uint32_t *ticket = P.ticket + 3, *exits = P.ticket + 5;
     // every chunk is 2048 bytes except possibly the last one; every chunk but chunk 0 has HALO bytes of look-behind
     const uint32_t last = nchunks - 1u;
     const uint32_t last_bytes = (uint32_t)(P.alen - (uint64_t)last * 2048u);   // 1 .. 2048
@@ -109,10 +218,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
 
     // lane 0 only: the next chunk of this warp.  The draw for the ticket after the current one is already in flight, so the
     // atomic's latency is never waited for.
-    // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3), so that a launch does not begin with thousands of
-    // atomics on one address; the counter hands out the chunks after those.
-    const uint32_t t_base = gridDim.x * NW * TICKET_CHUNKS;
-    uint32_t t_cur = 0, t_left = 0, t_next = (blockIdx.x * NW + warp) * TICKET_CHUNKS;
+    // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3 of the window), so that a launch does not begin with
+    // thousands of atomics on one address; the counter hands out the chunks after those.
+    const uint32_t t_base = chunk_begin + gridDim.x * NW * TICKET_CHUNKS;
+    uint32_t t_cur = 0, t_left = 0, t_next = chunk_begin + (blockIdx.x * NW + warp) * TICKET_CHUNKS;
     auto next_chunk = [&]() -> uint32_t {
         if (t_left == 0) {
             t_cur = t_next;
@@ -126,7 +235,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     // lane 0 only: refill buffer b with the warp's next chunk (bulk copy of the chunk and its look-behind), or mark the end
     auto fetch = [&](int b) {
         const uint32_t c = next_chunk();
-        if (c < nchunks) {
+        if (c < chunk_end) {
             my_chunk[b] = c;
             const uint32_t halo = c > 0u ? (uint32_t)Cfg::HALO : 0u;
             const uint32_t tx = (c == last ? last_tx : 2048u) + halo;
@@ -145,6 +254,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     __syncwarp();
     int b = 0;
     uint32_t phase = 0;
+    uint32_t parked = 0;           // lanes parked in `park` during the current run
+    bool u8_bad = false;
     while (true) {
         mbar_wait(bar0 + 8 * b, phase);
         const uint32_t c = my_chunk[b];
@@ -156,55 +267,36 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             const bool edge = (c == 0u) || (c == last && last_partial);
             chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, unresolved);
             __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
-            if (lane == 0) {
-                fetch(b);
-                if (unresolved) *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
-            }
-            warp_compute<UTF8, 1>(ph, in, lane, P, P.u8_slots + (size_t)c * (8 * 5));
+            if (lane == 0) fetch(b);
+            if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
+                *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
+            warp_compute<UTF8, 2>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
+            parked += (uint32_t)__popc(ph.u8_lanes);
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
-        __stcs(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)ph.m0);
-        __stcs(reinterpret_cast<unsigned long long *>(mp + 32), (unsigned long long)ph.m1);
-        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, ph.u8_lanes);
+        st_mask(mp, ph.m0);
+        st_mask(mp + 32, ph.m1);
+        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
         if (++b == DEPTH) {
             b = 0;
             phase ^= 1u;
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// UTF-8 validation of the lanes the classify kernel deferred.  Chunk c owns 8 slots of 5 x 16 bytes in P.u8_slots
-// ([chunk][slot 0..7][vector 0..4]); the first popc(summary word 3) of them hold, for the chunk's flagged lanes in lane
-// order, the 16 bit-plane words, the 4 bytes before the lane and its end-of-document bit.  One thread per slot.  A
-// violation stores the document generation into spec_flag[1]; the document's last launch (the persistent kernel in its
-// not-needed-as-fallback role) folds it into the verdict.  Runs on a second stream beside the scan and flatten launches.
-// ---------------------------------------------------------------------------------------------
-constexpr int U8_SLOTS = 8;           // == SJ_U8_DEFER_MAX
-constexpr int U8_SLOT_VECTORS = 5;
-static_assert(U8_SLOTS == SJ_U8_DEFER_MAX, "slot count and deferral limit must agree");
-
-__global__ void __launch_bounds__(256) stage1_utf8_lanes_kernel(const Stage1Params P, uint32_t nchunks) {
-    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t c = t / U8_SLOTS, slot = t % U8_SLOTS;
-    bool bad = false;
-    if (c < nchunks) {
-        const uint32_t lanes = __ldcg(P.chunk_sum + (size_t)c * 4 + 3);
-        if (slot < (uint32_t)__popc(lanes)) {
-            const uint4 *s = P.u8_slots + ((size_t)c * U8_SLOTS + slot) * U8_SLOT_VECTORS;
-            const uint4 a = __ldcs(s), b = __ldcs(s + 1), d = __ldcs(s + 2), e = __ldcs(s + 3), f = __ldcs(s + 4);
-            const uint32_t pl[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            const uint32_t ph[8] = {d.x, d.y, d.z, d.w, e.x, e.y, e.z, e.w};
-            Utf8Pre32 ul, uh;
-            utf8_pre32(pl, ul);
-            utf8_pre32(ph, uh);
-            const Utf8Carry uc = utf8_carry_from_prev_word(f.x);
-            uint32_t tail_must;
-            const uint64_t ue = utf8_errors64(ul, uh, uc, &tail_must);
-            bad = (ue != 0) || (f.y != 0 && tail_must != 0);
+        if (UTF8 && parked && ((c & (TICKET_CHUNKS - 1u)) == TICKET_CHUNKS - 1u || c + 1u == chunk_end)) {
+            // end of a run: the lanes whose validation was deferred, 32 at a time
+            __syncwarp();
+            u8_bad |= validate_parked_lanes(park, parked, lane);
+            parked = 0;
+            __syncwarp();
         }
     }
-    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) P.spec_flag[1] = P.gen;
+    // a violation among the deferred lanes: the document's last launch folds it into the verdict (stage1_persistent.cuh)
+    if (UTF8 && u8_bad && lane == 0) P.spec_flag[1] = P.gen;
+    // the last CTA to leave frees the chunk counter for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(exits, 1u) == gridDim.x - 1u) {
+        *ticket = 0;
+        *exits = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -261,26 +353,28 @@ __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint
 constexpr int SPAN_PER_THREAD = 4;                         // consecutive chunk summaries per thread
 constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
 
-__global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks) {
+// blocks [block_begin, block_begin + gridDim.x) of SPAN_BLOCK chunk summaries each (a window of the pipeline)
+__global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks, uint32_t block_begin) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.ticket[3] = 0;   // the classify kernel is done: its chunk counter is free again
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
-    const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
+    const uint32_t blk = block_begin + blockIdx.x;
+    const uint32_t c0 = blk * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     SpanAcc mine = span_empty();
 #pragma unroll
     for (int k = 0; k < SPAN_PER_THREAD; k++)
         if (c0 + k < nchunks) mine = span_concat(mine, span_from_summary(reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k]));
     SpanAcc total;
     block_span_inclusive(mine, s_w, total);
-    if (threadIdx.x == 0) reinterpret_cast<uint4 *>(P.block_sum)[blockIdx.x] = make_uint4(total.c[0], total.c[1], span_flags(total), 0u);
+    if (threadIdx.x == 0) reinterpret_cast<uint4 *>(P.block_sum)[blk] = make_uint4(total.c[0], total.c[1], span_flags(total), 0u);
 }
 
-__global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1Params P, uint32_t nchunks) {
+__global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1Params P, uint32_t nchunks, uint32_t block_begin) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
-    const uint32_t c0 = blockIdx.x * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
+    const uint32_t blk = block_begin + blockIdx.x;
+    const uint32_t c0 = blk * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     uint4 sum[SPAN_PER_THREAD];
     SpanAcc mine = span_empty();
 #pragma unroll
@@ -288,11 +382,11 @@ __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1P
         sum[k] = c0 + k < nchunks ? reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k] : make_uint4(0u, 0u, 0u, 0u);
         mine = span_concat(mine, span_from_summary(sum[k]));
     }
-    // everything before this block: ordered reduction of the block aggregates 0 .. blockIdx.x-1
+    // everything before this block: ordered reduction of the block aggregates 0 .. blk-1 (earlier windows included)
     SpanAcc before = span_empty();
-    for (uint32_t b0 = 0; b0 < blockIdx.x; b0 += 1024u) {
+    for (uint32_t b0 = 0; b0 < blk; b0 += 1024u) {
         const uint32_t j = b0 + threadIdx.x;
-        const SpanAcc bj = j < blockIdx.x ? span_from_summary(reinterpret_cast<const uint4 *>(P.block_sum)[j]) : span_empty();
+        const SpanAcc bj = j < blk ? span_from_summary(reinterpret_cast<const uint4 *>(P.block_sum)[j]) : span_empty();
         SpanAcc total;
         block_span_inclusive(bj, s_w, total);
         before = span_concat(before, total);

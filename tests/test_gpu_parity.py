@@ -212,11 +212,13 @@ def test_adversarial_corpus_every_kernel_organisation(dev, scratch, kernel, warp
 
 
 def test_stream_pipeline_speculation_and_fallback(dev, scratch):
-    """The stream pipeline gives up when a backslash run covers the 32 bytes before a 2 KiB chunk; the persistent kernel
-    behind it must then produce the document (and must stay out of the way otherwise)."""
-    for run in (0, 1, 30, 31, 32, 33, 64, 65, 2047, 2048, 2049, 5000):
+    """A backslash run that covers the 32 bytes before a 2 KiB chunk is walked back through global memory (up to 64 KiB);
+    only a longer one makes the stream pipeline give up, and the persistent kernel behind it must then produce the
+    document (and must stay out of the way otherwise)."""
+    for run in (0, 1, 30, 31, 32, 33, 64, 65, 511, 512, 513, 2047, 2048, 2049, 5000, 65535, 65536, 65537, 66047, 66048, 66049, 70001, 200000):
         for pad in (2048 - 2, 2048 - 1, 2048, 4096 - 33, 4096 - 1):
-            head = b'["' + b"a" * (pad - 2 - run) if pad - 2 - run >= 0 else b'["'
+            lead = (pad - 2 - run) % 2048   # the run always ends `pad` mod 2 KiB
+            head = b'["' + b"a" * lead
             data = head + b"\\" * 0 + b"\\"[:1] * run + b'"x", "y\\"", 1, {"k": "\\\\"}]' + b" " * 3000 + b"[]"
             want = oracle.stage1(data, impl="ref")
             for kernel in ("stream", "fused", "persistent"):
@@ -227,14 +229,32 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
                     raise AssertionError(f"run={run} pad={pad} kernel={kernel}") from e
     # alternate documents that do / do not trigger the fallback: no state may leak between calls
     ok = b'{"a": [1, 2, 3], "b": "' + b"z" * 9000 + b'"}'
-    bad = b'["' + b"a" * 2040 + b"\\"[:1] * 200 + b'" ]'
-    wok, wbad = oracle.stage1(ok), oracle.stage1(bad)
+    bad = b'["' + b"a" * 2046 + b"\\"[:1] * (2048 * 40 + 1) + b'" ]'   # 80 KiB + 1 backslashes ending on a chunk boundary
+    walk = b'["' + b"a" * 2040 + b"\\"[:1] * 200 + b'" ]'               # resolved by the walk
+    wok, wbad, wwalk = oracle.stage1(ok), oracle.stage1(bad, impl="fast"), oracle.stage1(walk)
     for kernel in ("stream", "fused"):
         for _ in range(6):
             res, out = run_device(dev, scratch, ok, kernel=kernel)
             assert_same(res, out, wok)
             res, out = run_device(dev, scratch, bad, kernel=kernel)
             assert_same(res, out, wbad)
+            res, out = run_device(dev, scratch, walk, kernel=kernel)
+            assert_same(res, out, wwalk)
+    # the walk must stop at the first byte of the document: backslashes in the memory before it are not input
+    data = b"\\"[:1] * 4095 + b'"' + b'"abc"' + b" " * 3000 + b"[1]"
+    want = oracle.stage1(data, impl="ref")
+    for mis in (0, 1, 7, 15):
+        for kernel in ("stream", "fused", "persistent"):
+            dev.set_kernel(kernel)
+            dev.set_warps(8)
+            scratch.inp[: mis + len(data) + 64].fill_(0x5C)
+            view = scratch.inp[mis : mis + len(data)]
+            view.copy_(torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()))
+            scratch.out[: len(data) + 8].fill_(-1)
+            res = dev.index(view, scratch.out)
+            dev.set_kernel("auto")
+            dev.set_warps(0)
+            assert_same(res, scratch.out, want)
 
 
 @pytest.mark.parametrize("kernel", ["fused", "stream", "split", "persistent"])
