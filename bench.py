@@ -139,7 +139,7 @@ def parse_args():
     ap.add_argument("--seg-bytes", type=int, default=GIB, help="N > 1: segment size")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--warps", type=int, default=0, help="force tile shape (2/4/8/16/24), 0 = auto")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "split", "stream", "fused"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "split", "stream"],
                     help="force the kernel organisation (sjb200_ctx_set_kernel); auto = the library's choice")
     ap.add_argument("--no-utf8", action="store_true", help="skip UTF-8 validation (the reference validates nothing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -356,10 +356,9 @@ def kernel_kind_for(args, seg_bytes: int) -> str:
 
 
 KERNEL_NAMES = {
-    "stream": "stage-1 stream pipeline, 6 launches per document: stage1_stream_classify_kernel -> stage1_utf8_lanes_kernel -> "
-              "stage1_span_reduce_kernel -> stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)",
+    "stream": "stage-1 stream pipeline, 5 launches per document: stage1_stream_classify_kernel -> stage1_span_reduce_kernel -> "
+              "stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)",
     "persistent": "stage1_persistent_kernel", "split": "stage1_classify_kernel + stage1_flatten_kernel",
-    "fused": "stage1_fused_kernel (classify / scan / flatten interleaved in one persistent launch; + stage1_persistent_kernel as a no-op fallback)",
 }
 
 

@@ -83,32 +83,30 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
 int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
 /*
  * Force the kernel organisation (tuning / test knob; every choice produces identical results):
- *   AUTO        chosen from the document size: PERSISTENT below 8 MiB and for the chunked host path, FUSED from 8 MiB on
+ *   AUTO        chosen from the document size: PERSISTENT below 48 MiB and for the chunked host path, SPLIT from 48 MiB,
+ *               STREAM from 160 MiB on
  *   PERSISTENT  persistent CTAs of compute warps + a scan warp over tiles, classify and flatten of a tile fused, decoupled
  *               look-back between tiles; needs no scratch
  *   SPLIT       two launches: classify (masks + per-chunk carries to L2 / HBM), then flatten
- *   STREAM      five launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp, a kernel that
- *               validates the UTF-8 of sparse non-ASCII lanes on an internal stream, two scan kernels over the chunk
- *               summaries, flatten
- *   FUSED       one persistent launch in which every warp alternates between classifying a run of chunks and flattening
- *               an older run whose block has been scanned meanwhile (decoupled look-back between blocks of 64 chunks);
- *               UTF-8 of sparse non-ASCII lanes is validated by the classifying warp itself, 32 lanes at a time
- * STREAM and FUSED resolve the escape state entering a chunk from a bounded look-behind (STREAM: 32 bytes; FUSED: 32
- * bytes, then a walk back of up to 64 KiB); a longer backslash run makes the PERSISTENT kernel, enqueued behind them on
+ *   STREAM      four launches, no waiting anywhere: classify with one private bulk-copy pipeline per warp (UTF-8 of sparse
+ *               non-ASCII lanes validated by the same warp, 32 lanes at a time), two scan kernels over the chunk summaries,
+ *               flatten
+ * STREAM resolves the escape state entering a chunk from a 32-byte look-behind and, if a backslash run fills it, a walk
+ * back through global memory of up to 64 KiB; a longer run makes the PERSISTENT kernel, enqueued behind the pipeline on
  * every call and otherwise returning at once, redo the document (same results).
- * SPLIT / STREAM / FUSED use scratch in device memory (0.26 bytes per input byte: mask planes, chunk summaries, carry words;
- * STREAM another 0.31 for parked UTF-8 lanes), allocated with the stream-ordered allocator on first use and grown when a
- * larger document arrives (no call synchronises for it); sjb200_ctx_reserve allocates it ahead of time.  If the allocation
- * fails an explicit choice returns MEMALLOC, the automatic choice stays with PERSISTENT.
- * Values 1 and 3 named two organisations of round 1 that were measured, rejected and removed: UNEXPECTED_ERROR.
+ * SPLIT / STREAM use scratch in device memory (0.26 bytes per input byte: mask planes, chunk summaries, carry words),
+ * allocated with the stream-ordered allocator on first use and grown when a larger document arrives (no call synchronises
+ * for it); sjb200_ctx_reserve allocates it ahead of time.  If the allocation fails an explicit choice returns MEMALLOC, the
+ * automatic choice stays with PERSISTENT.
+ * Values 1, 3 and 6 named organisations that were measured, rejected and removed (one tile per CTA, in-CTA dataflow,
+ * fused single launch; profiles/r2_overlap_experiments.txt): UNEXPECTED_ERROR.
  */
 #define SJB200_KERNEL_AUTO 0
 #define SJB200_KERNEL_PERSISTENT 2
 #define SJB200_KERNEL_SPLIT 4
 #define SJB200_KERNEL_STREAM 5
-#define SJB200_KERNEL_FUSED 6
 int32_t sjb200_ctx_set_kernel(sjb200_ctx *ctx, int32_t kind);
-/* Allocates the scratch for documents of up to `len` bytes now (flags bit 0: also for the STREAM organisation), so that
+/* Allocates the scratch for documents of up to `len` bytes now (flags: reserved, pass 0), so that
  * no later call has to.  MEMALLOC if it cannot be had. */
 int32_t sjb200_ctx_reserve(sjb200_ctx *ctx, uint64_t len, uint32_t flags);
 /* Chunk size (bytes, >= 4096) of the streaming host path of sjb200_stage1: the document travels to the device in chunks

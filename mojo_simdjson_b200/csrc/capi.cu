@@ -12,7 +12,6 @@
 #include "stage1_persistent.cuh"
 #include "stage1_split.cuh"
 #include "stage1_stream.cuh"
-#include "stage1_fused.cuh"
 
 #ifndef SJ_K3_FW
 #define SJ_K3_FW 4   // warps (= chunks) per CTA of the flatten kernel (2 and 4: +0.8 % over 8, 16: -2 %)
@@ -26,8 +25,8 @@ constexpr uint32_t RESULT_SLOTS = 256;
 constexpr uint64_t MIN_TILE = 2 * 2048;
 // Kernel organisation by document size (device-resident documents; tools/sizesweep.py, measured): the persistent tile kernel
 // for small documents (all 148 SMs get a tile even at a few hundred KiB), the split pair from SPLIT_MIN_BYTES, the stream
-// pipeline from STREAM_MIN_BYTES.  The fused kernel (stage1_fused.cuh) is selectable but never chosen automatically: it
-// measured slower than the pipeline at every size (1 GiB: 1145 vs 1871 GB/s; 64 MiB: 872 vs 1192 GB/s for the split pair).
+// pipeline from STREAM_MIN_BYTES.  (A fused single-launch organisation and a windowed two-stream pipeline were measured in
+// round 2 and removed again: profiles/r2_overlap_experiments.txt.)
 constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
 constexpr uint64_t STREAM_MIN_BYTES = 160ull << 20;
 
@@ -47,12 +46,8 @@ inline int32_t cuda_err(cudaError_t e) {
 struct Knobs {
     int pdl = 1;            // SJB200_PDL=0: no programmatic dependent launch between the launches of a document
     int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
-    int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream|fused
+    int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream
     uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
-    uint32_t window_chunks = (64u << 20) / 2048u;   // SJB200_WINDOW_MIB: window of the stream pipeline (0 = the whole document)
-    int corun = 0;          // SJB200_EXPERIMENT_CORUN=1: TIMING EXPERIMENT ONLY -- flatten runs beside classify on the masks / carries the
-                            // previous pass over the same document left behind (an upper bound for any overlapped organisation)
-    int classify_ctas = 2;  // SJB200_CLASSIFY_CTAS: resident classify CTAs per SM (the flatten kernel of the previous window fills the rest)
 };
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24; }
 const Knobs &knobs() {
@@ -64,16 +59,9 @@ const Knobs &knobs() {
             if (strcmp(e, "persist") == 0) v.kernel = SJB200_KERNEL_PERSISTENT;
             if (strcmp(e, "split") == 0) v.kernel = SJB200_KERNEL_SPLIT;
             if (strcmp(e, "stream") == 0) v.kernel = SJB200_KERNEL_STREAM;
-            if (strcmp(e, "fused") == 0) v.kernel = SJB200_KERNEL_FUSED;
         }
         if (const char *e = getenv("SJB200_CHUNK_MIB"))
             if (atoi(e) > 0) v.chunk_bytes = (uint64_t)atoi(e) << 20;
-        if (const char *e = getenv("SJB200_WINDOW_MIB")) {
-            const uint64_t mib = (uint64_t)(atoi(e) > 0 ? atoi(e) : 0);
-            v.window_chunks = (uint32_t)(((mib << 20) / 2048u + SPAN_BLOCK - 1) / SPAN_BLOCK * SPAN_BLOCK);   // whole scan blocks (8 MiB)
-        }
-        if (const char *e = getenv("SJB200_CLASSIFY_CTAS")) v.classify_ctas = atoi(e);
-        if (const char *e = getenv("SJB200_EXPERIMENT_CORUN")) v.corun = atoi(e);
         return v;
     }();
     return k;
@@ -103,21 +91,15 @@ struct sjb200_ctx {
     int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
     int split_occ[2] = {0, 0};             // same for the classify kernel of the split pair, NW = 8, 16
     int stream_occ = 0;                    // same for the stream classify kernel
-    int fused_occ = 0;                     // same for the fused kernel
-    // scratch of the split / stream / fused organisations, sized for `scratch_chunks` 2 KiB chunks (sjb200_ctx_reserve, or
+    // scratch of the split / stream organisations, sized for `scratch_chunks` 2 KiB chunks (sjb200_ctx_reserve, or
     // grown on demand with the stream-ordered allocator: no call ever synchronises for it)
     uint64_t *d_masks = nullptr;           // the two structural mask planes of every chunk (512 B per chunk)
     uint64_t *d_carry = nullptr;           // one carry word per chunk
     uint32_t *d_chunk_sum = nullptr;       // 16-byte chunk summaries
     uint32_t *d_block_sum = nullptr;       // stream pipeline: the same per 4096 chunks
-    uint32_t *d_blk_state = nullptr;       // fused kernel: blk_done[], blk_ready[] and its own look-back descriptors
     uint64_t scratch_chunks = 0;
     bool scratch_failed = false;           // an allocation failed once: automatic choice stays with the persistent kernel
     uint32_t *d_spec_flag = nullptr;       // [0] speculation failed, [1] deferred UTF-8 violation (generation valued)
-    cudaStream_t aux_stream = nullptr;     // stream pipeline: the deferred UTF-8 lanes are validated here, beside the scan
-    cudaEvent_t ev_join = nullptr;
-    static constexpr int MAX_WINDOWS = 64;
-    cudaEvent_t win_ev[MAX_WINDOWS] = {};  // stream pipeline: classify of window w is done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t launches = 0;
@@ -164,7 +146,6 @@ cudaError_t prepare_split(int *occ) {
 #define SJ_STREAM_NW 8
 #endif
 constexpr int STREAM_NW = SJ_STREAM_NW;
-constexpr int FUSED_NW = SJ_FUSED_NW;
 cudaError_t prepare_stream(int *occ) {
     using Cfg = StreamCfg<STREAM_NW>;
     // every kernel of the pipeline asks for the same shared-memory carve-out: kernels with different L1 / shared splits
@@ -174,11 +155,6 @@ cudaError_t prepare_stream(int *occ) {
     cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
-cudaError_t prepare_fused(int *occ) {
-    using Cfg = FusedCfg<FUSED_NW>;
-    return prepare_kernel(stage1_fused_kernel<FUSED_NW, true>, stage1_fused_kernel<FUSED_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
-}
-
 template <int NW, bool UTF8>
 cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = PersistCfg<NW>;
@@ -216,72 +192,25 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
     return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
 }
-// The stream pipeline (stage1_stream.cuh): per window classify on `s`; scan + flatten of the window on the context's second
-// stream behind it, i.e. beside the classify launch of the next window.  `s` finally waits for the second stream.
+// The stream pipeline (stage1_stream.cuh): classify -> span_reduce -> span_carries -> flatten, stream ordered; the dependent
+// launches overlap their launch latency with their predecessor (programmatic dependent launch).
 template <bool UTF8>
 cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = StreamCfg<STREAM_NW>;
     constexpr int FW = SJ_K3_FW;
-    const Knobs &k = knobs();
-    const bool pdl = k.pdl != 0;
+    const bool pdl = knobs().pdl != 0;
     const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
-    uint32_t win = k.window_chunks ? k.window_chunks : nchunks;                 // chunks per window, a multiple of SPAN_BLOCK
-    if ((nchunks + win - 1) / win > (uint32_t)sjb200_ctx::MAX_WINDOWS) win = (((nchunks + sjb200_ctx::MAX_WINDOWS - 1) / sjb200_ctx::MAX_WINDOWS + SPAN_BLOCK - 1) / SPAN_BLOCK) * SPAN_BLOCK;
-    const uint32_t nwin = (nchunks + win - 1) / win;
-    const bool two_streams = nwin > 1;
-    cudaStream_t s2 = two_streams ? c->aux_stream : s;
-    cudaError_t e = cudaSuccess;
-    if (k.corun) {   // timing experiment (see Knobs::corun): classify + scans on s, flatten of the whole document on the second stream at once
-        e = cudaEventRecord(c->win_ev[0], s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, c->win_ev[0], 0);
-        const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
-        const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
-        if (e == cudaSuccess) {
-            stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, 0u, nchunks);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, c->aux_stream, false, p, 0u, nchunks);
-        const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
-        if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
-        if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
-        if (e == cudaSuccess) e = cudaEventRecord(c->ev_join, c->aux_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_join, 0);
-        c->launches += 4;
-        return e;
-    }
-    for (uint32_t w = 0; w < nwin && e == cudaSuccess; w++) {
-        const uint32_t cb = w * win, ce = cb + win < nchunks ? cb + win : nchunks;
-        const unsigned want = (ce - cb + STREAM_NW - 1) / STREAM_NW;
-        const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
-        stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, cb, ce);
-        e = cudaGetLastError();
-        if (e == cudaSuccess && two_streams) {
-            e = cudaEventRecord(c->win_ev[w], s);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, c->win_ev[w], 0);
-        }
-        const unsigned b0 = cb / SPAN_BLOCK, nblocks = (ce - cb + SPAN_BLOCK - 1) / SPAN_BLOCK;
-        // the first launch behind an event wait is an ordinary one; the two after it overlap their launch latency with their
-        // predecessor (programmatic dependent launch)
-        if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s2, pdl && !two_streams, p, nchunks, b0);
-        if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s2, pdl, p, nchunks, b0);
-        if (e == cudaSuccess)
-            e = launch_dependent(stage1_flatten_kernel<FW>, (ce - cb + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s2, pdl, p, cb, ce);
-    }
-    if (e == cudaSuccess && two_streams) {
-        e = cudaEventRecord(c->ev_join, s2);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_join, 0);   // before the document's last launch (and the next document)
-    }
-    c->launches += 4ull * nwin;
-    return e;
-}
-template <bool UTF8>
-cudaError_t launch_fused(const Stage1Params &p, cudaStream_t s, int max_ctas) {
-    using Cfg = FusedCfg<FUSED_NW>;
-    const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
-    const unsigned want = (nchunks + FUSED_NW * TICKET_CHUNKS - 1) / (FUSED_NW * TICKET_CHUNKS);
+    const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
-    stage1_fused_kernel<FUSED_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks);
-    return cudaGetLastError();
+    stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, 0u, nchunks);
+    cudaError_t e = cudaGetLastError();
+    const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
+    if (e == cudaSuccess)
+        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
+    c->launches += 4;
+    return e;
 }
 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
@@ -298,9 +227,8 @@ int pick_warps(const sjb200_ctx *c, uint64_t alen) {
 // everything) or, on the streaming host path, by several launches over consecutive tile ranges sharing the generation.
 struct DocPlan {
     Stage1Params p;
-    uint64_t *fdesc; // look-back descriptors of the fused kernel's blocks (its fallback, the persistent kernel, keeps p.desc)
     int warps;       // tile shape of the persistent kernel (also the exact fallback of the speculating organisations)
-    int kind;        // SJB200_KERNEL_PERSISTENT / SPLIT / STREAM / FUSED
+    int kind;        // SJB200_KERNEL_PERSISTENT / SPLIT / STREAM
     bool utf8;
 };
 
@@ -310,9 +238,8 @@ void free_scratch(sjb200_ctx *c, cudaStream_t s) {
     if (c->d_carry) cudaFreeAsync(c->d_carry, s);
     if (c->d_chunk_sum) cudaFreeAsync(c->d_chunk_sum, s);
     if (c->d_block_sum) cudaFreeAsync(c->d_block_sum, s);
-    if (c->d_blk_state) cudaFreeAsync(c->d_blk_state, s);
     c->d_masks = c->d_carry = nullptr;
-    c->d_chunk_sum = c->d_block_sum = c->d_blk_state = nullptr;
+    c->d_chunk_sum = c->d_block_sum = nullptr;
     c->scratch_chunks = 0;
 }
 
@@ -327,13 +254,10 @@ cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, cudaStream_t s) {
     const uint64_t max_chunks = (c->max_len + 16) / 2048 + 64;
     if (n > max_chunks) n = max_chunks > chunks + 64 ? max_chunks : chunks + 64;
     free_scratch(c, s);
-    const uint64_t nblk = n / BLOCK_CHUNKS + 2;
     cudaError_t e = cudaMallocAsync(&c->d_masks, n * 512, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_carry, n * 8, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_chunk_sum, n * 16, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_blk_state, nblk * 16, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_blk_state, 0, nblk * 16, s);
     if (e != cudaSuccess) {
         free_scratch(c, s);
         cudaGetLastError();
@@ -347,7 +271,6 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
                       uint32_t flags, uint32_t slot, int32_t *d_status, bool whole_document = true) {
     Stage1Params &p = d.p;
     memset(&p, 0, sizeof p);
-    d.fdesc = nullptr;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(d_buf);
     p.mis = (uint32_t)(addr & 15u);
     p.abase = d_buf - p.mis;
@@ -364,7 +287,6 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
         cudaMemsetAsync(c->ticket, 0, 256, c->stream);
         cudaMemsetAsync(c->d_spec_flag, 0, 256, c->stream);
-        if (c->d_blk_state) cudaMemsetAsync(c->d_blk_state, 0, (c->scratch_chunks / BLOCK_CHUNKS + 2) * 16, c->stream);
         c->gen = 1;
     }
     p.gen = c->gen;
@@ -405,18 +327,14 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
     p.ntiles = (uint32_t)ntiles;
     p.tile_begin = 0;
     p.tile_end = p.ntiles;
-    p.ticket = c->ticket;   // [0],[1] alternate between persistent launches, [3..5] serve the stream / fused kernels
+    p.ticket = c->ticket;   // [0],[1] alternate between persistent launches, [3] and [5] serve the stream pipeline
     if (kind != SJB200_KERNEL_PERSISTENT) {
         p.masks = c->d_masks;
         p.carry = c->d_carry;
         p.chunk_sum = c->d_chunk_sum;
         p.block_sum = c->d_block_sum;
-        const uint64_t nblk = c->scratch_chunks / BLOCK_CHUNKS + 2;
-        p.blk_done = c->d_blk_state;
-        p.blk_ready = c->d_blk_state + nblk;
-        d.fdesc = reinterpret_cast<uint64_t *>(c->d_blk_state + 2 * nblk);
     }
-    if (kind == SJB200_KERNEL_STREAM || kind == SJB200_KERNEL_FUSED) p.spec_flag = c->d_spec_flag;
+    if (kind == SJB200_KERNEL_STREAM) p.spec_flag = c->d_spec_flag;
     return SJB200_SUCCESS;
 }
 
@@ -442,18 +360,9 @@ int32_t launch_range(sjb200_ctx *c, DocPlan &d, uint32_t tile_begin, uint32_t ti
     const bool utf8 = d.utf8;
     const bool whole = tile_begin == 0 && tile_end == d.p.ntiles;
     cudaError_t e = cudaSuccess;
-    const bool speculating = (d.kind == SJB200_KERNEL_STREAM || d.kind == SJB200_KERNEL_FUSED) && whole;
+    const bool speculating = d.kind == SJB200_KERNEL_STREAM && whole;
     if (speculating) {
-        if (d.kind == SJB200_KERNEL_STREAM) {
-            int per_sm = c->stream_occ;
-            if (knobs().classify_ctas > 0 && knobs().classify_ctas < per_sm) per_sm = knobs().classify_ctas;
-            e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * per_sm) : launch_stream<false>(c, p, stream, c->sm_count * per_sm);
-        } else {
-            Stage1Params pf = p;
-            pf.desc = d.fdesc;
-            e = utf8 ? launch_fused<true>(pf, stream, c->sm_count * c->fused_occ) : launch_fused<false>(pf, stream, c->sm_count * c->fused_occ);
-            c->launches += 1;
-        }
+        e = utf8 ? launch_stream<true>(c, p, stream, c->sm_count * c->stream_occ) : launch_stream<false>(c, p, stream, c->sm_count * c->stream_occ);
         // ... then the persistent kernel as the exact fallback: returns at once unless a chunk raised the speculation flag
     } else {
         p.spec_flag = nullptr;   // the persistent kernel alone indexes this range
@@ -721,12 +630,8 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
     if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
     if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
-    if (e == cudaSuccess) e = prepare_fused(&c->fused_occ);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_spec_flag, 256);
     if (e == cudaSuccess) e = cudaMemset(c->d_spec_flag, 0, 256);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
-    for (int w = 0; w < sjb200_ctx::MAX_WINDOWS && e == cudaSuccess; w++) e = cudaEventCreateWithFlags(&c->win_ev[w], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -759,10 +664,6 @@ int32_t sjb200_ctx_destroy(sjb200_ctx *c) {
     for (int k = 0; k < sjb200_ctx::MAX_CHUNKS; k++)
         if (c->chunk_ev[k]) cudaEventDestroy(c->chunk_ev[k]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (int w = 0; w < sjb200_ctx::MAX_WINDOWS; w++)
-        if (c->win_ev[w]) cudaEventDestroy(c->win_ev[w]);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -781,8 +682,7 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *c, void *cuda_stream) {
 
 int32_t sjb200_ctx_set_kernel(sjb200_ctx *c, int32_t kind) {
     if (!c) return SJB200_UNINITIALIZED;
-    if (kind != SJB200_KERNEL_AUTO && kind != SJB200_KERNEL_PERSISTENT && kind != SJB200_KERNEL_SPLIT && kind != SJB200_KERNEL_STREAM &&
-        kind != SJB200_KERNEL_FUSED)
+    if (kind != SJB200_KERNEL_AUTO && kind != SJB200_KERNEL_PERSISTENT && kind != SJB200_KERNEL_SPLIT && kind != SJB200_KERNEL_STREAM)
         return SJB200_UNEXPECTED_ERROR;
     c->kernel_kind = kind;
     return SJB200_SUCCESS;

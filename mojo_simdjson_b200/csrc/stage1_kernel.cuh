@@ -82,13 +82,10 @@ struct Stage1Params {
     uint32_t flags;         // bit0: fold the UTF-8 verdict into the error code
     uint64_t *masks;        // split pair only: [chunk][parity][lane] structural masks, 512 bytes per 2 KiB chunk
     uint64_t *carry;        // split pair only: per chunk, bit 63 = starts inside a string, bits 0..39 = rank of its first index
-    uint4 *u8_slots;        // stream pipeline only: per chunk 8 slots x 5 x 16 B for lanes whose UTF-8 validation is deferred
     uint32_t *chunk_sum;    // stream pipeline only: 16 bytes per chunk {count0, count1, flags, 0}
     uint32_t *block_sum;    // stream pipeline only: the same per 1024 chunks
     uint32_t *spec_flag;    // stream pipeline: == gen once a chunk could not resolve its escape carry locally.  Persistent
                             // kernel: if non-null, run only when *spec_flag == gen (it is the exact fallback)
-    uint32_t *blk_done;     // fused kernel: chunks classified so far per block of 64 chunks (returns to 0 when the block is scanned)
-    uint32_t *blk_ready;    // fused kernel: == gen once the block's carry words are written
     uint64_t *trace;        // debug builds (-DSJ_TRACE=1): 16 x u64 of timestamps per tile, else unused
 };
 
@@ -296,7 +293,7 @@ struct LanePhase1 {
     uint32_t wc0, wc1;
     uint32_t wflags;  // bit0 quote parity, bit1/2 unescaped control (outside/inside), bit3 UTF-8 violation
     uint32_t tail;    // bit0 e_out, bit1 p_out after the warp's last byte
-    uint32_t u8_lanes;  // stream pipeline: lanes whose UTF-8 validation is left to stage1_utf8_lanes_kernel (else 0)
+    uint32_t u8_lanes;  // stream pipeline: lanes parked for deferred UTF-8 validation (else 0)
 };
 
 // every shared-memory read of the input happens here (the persistent kernel frees the buffer right after)
@@ -332,16 +329,15 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
 
 // DEFER_U8: when only a few lanes of the warp hold (or directly follow) bytes >= 0x80, do not validate UTF-8 here -- the
 // whole warp would pay ~75 ALU instructions for them -- but park those lanes (16 bit-plane words, the 4 bytes before the
-// lane, its end-of-document bit: 80 B) and report them; they are validated later 32 at a time:
-//   DEFER_U8 == 1 : parked in global memory, validated by stage1_utf8_lanes_kernel (stage1_stream.cuh)
-//   DEFER_U8 == 2 : parked in the warp's own shared-memory slots, validated by the same warp at the end of its run of
-//                   chunks (stage1_fused.cuh); `u8_slots` then points at the first free slot
+// lane, its end-of-document bit: 80 B) in the warp's own shared-memory slots and report them; the same warp validates them
+// 32 at a time at the end of its run of chunks (stage1_stream.cuh: validate_parked_lanes).  `u8_slots` points at the
+// first free slot.  DEFER_U8 == 0: always validate inline.
 #ifndef SJ_U8_DEFER_MAX
 #define SJ_U8_DEFER_MAX 8
 #endif
 template <bool UTF8, int DEFER_U8 = 0>
 __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P,
-                                             uint4 *u8_slots = nullptr /* DEFER_U8: 8 free slots of 5 uint4 */) {
+                                             uint4 *u8_slots = nullptr /* DEFER_U8: the warp's free shared-memory slots, 5 uint4 each */) {
     LaneMasks m;
     uint32_t u8err = 0;
     r.u8_lanes = 0;
@@ -368,19 +364,11 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 r.u8_lanes = hi_lanes;
                 if (any_hi) {
                     uint4 *s = u8_slots + 5 * __popc(hi_lanes & ((1u << lane) - 1u));   // 80 contiguous bytes per slot
-                    if (DEFER_U8 == 2) {
-                        s[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        s[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-                        s[2] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        s[3] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-                        s[4] = make_uint4(in.prev, in.ends, 0u, 0u);
-                    } else {
-                        __stcs(s + 0, make_uint4(pl[0], pl[1], pl[2], pl[3]));
-                        __stcs(s + 1, make_uint4(pl[4], pl[5], pl[6], pl[7]));
-                        __stcs(s + 2, make_uint4(ph[0], ph[1], ph[2], ph[3]));
-                        __stcs(s + 3, make_uint4(ph[4], ph[5], ph[6], ph[7]));
-                        __stcs(s + 4, make_uint4(in.prev, in.ends, 0u, 0u));
-                    }
+                    s[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    s[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                    s[2] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    s[3] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                    s[4] = make_uint4(in.prev, in.ends, 0u, 0u);
                 }
             } else if (hi_lanes) {
                 Utf8Pre32 ul, uh;

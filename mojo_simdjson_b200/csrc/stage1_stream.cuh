@@ -1,6 +1,5 @@
-// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of stream-ordered launches with no
-// waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them).
-// The document is cut into WINDOWS (64 MiB by default); for every window, in this order:
+// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of four stream-ordered launches with no
+// waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them):
 //
 //   stream_classify : every warp is its own pipeline.  A warp draws runs of 4 consecutive 2 KiB chunks from an atomic
 //                     counter, each chunk fetched with its own bulk copy (cp.async.bulk, DEPTH chunks in flight per warp, one
@@ -10,16 +9,21 @@
 //                     lanes per chunk with bytes >= 0x80 park their bit planes in the warp's shared-memory slots and are
 //                     validated 32 at a time at the end of the run (instead of one warp per lane).
 //   span_reduce     : 4096 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
-//   span_carries    : block prefix from the block aggregates of this and all earlier windows, then the same local scan ->
-//                     one carry word per chunk (bit 63 = starts inside a string, bits 0..39 = rank of its first index);
-//                     the last window writes the verdict.
+//   span_carries    : block prefix from the block aggregates, then the same local scan -> one carry word per chunk
+//                     (bit 63 = starts inside a string, bits 0..39 = rank of its first index) and the verdict.
 //   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
 //
-// The classify launches of consecutive windows follow each other on the context's stream; scan + flatten of window w run on
-// a second stream behind classify(w), i.e. BESIDE classify(w+1): the classify kernel is bound by the ALU pipe and is
-// launched at half occupancy, the flatten kernel is bound by shared memory / XU / issue slots and fills the other half of
-// every SM.  A window's mask planes (16 MiB) are written and read back inside the 126 MB L2.
+// The carries a 32-byte look-behind cannot decide are the escape state after a backslash run that covers all of it and the
+// scalar state after a quote preceded by 31 backslashes.  A chunk that sees either walks back through global memory
+// until the run ends (backslash_run_global, up to WALK_MAX = 64 KiB).  Only a run longer than that raises `spec_flag`
+// (stores the document generation); the later launches then do nothing and the persistent kernel, enqueued behind them
+// with Stage1Params::spec_flag set, redoes the document exactly.  Otherwise that kernel returns at once.  Results are
+// identical either way.
 //
+// Overlapping classify (ALU pipe) with flatten (shared memory / XU) was measured in round 2 -- windows on two streams, and
+// the two kernels side by side with no dependency at all as an upper bound -- and is worth 2 % at best: the pass as a
+// whole is bound by instruction issue (profiles/r2_overlap_experiments.txt).
+// Reference: json_structural_indexer.mojo:83-186 (step / next / finish), restated in oracle/stage1_oracle.c.
 #pragma once
 #include "stage1_split.cuh"
 
@@ -30,7 +34,7 @@
 #define SJ_STREAM_DEPTH 3
 #endif
 #ifndef SJ_MASK_STORE
-#define SJ_MASK_STORE 0   // 0: write-back stores (the planes stay in L2 for the flatten kernel of the same window), 1: streaming stores
+#define SJ_MASK_STORE 1   // 1: streaming stores (the planes of a large document do not fit the L2 anyway), 0: write-back stores
 #endif
 
 namespace sjb200 {
@@ -192,7 +196,7 @@ __device__ __forceinline__ bool validate_parked_lanes(const uint8_t *park, uint3
     return __any_sync(0xFFFFFFFFu, bad);
 }
 
-// chunks [chunk_begin, chunk_end) of the document (a window of the pipeline; chunk_begin is a multiple of TICKET_CHUNKS)
+// chunks [chunk_begin, chunk_end) of the document (chunk_begin a multiple of TICKET_CHUNKS; the pipeline passes the whole document)
 template <int NW, bool UTF8>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks,
                                                                                                             uint32_t chunk_begin, uint32_t chunk_end) {
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             if (lane == 0) fetch(b);
             if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
                 *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
-            warp_compute<UTF8, 2>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
+            warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
             parked += (uint32_t)__popc(ph.u8_lanes);
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
@@ -353,7 +357,7 @@ __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint
 constexpr int SPAN_PER_THREAD = 4;                         // consecutive chunk summaries per thread
 constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
 
-// blocks [block_begin, block_begin + gridDim.x) of SPAN_BLOCK chunk summaries each (a window of the pipeline)
+// blocks [block_begin, block_begin + gridDim.x) of SPAN_BLOCK chunk summaries each
 __global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks, uint32_t block_begin) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1P
         sum[k] = c0 + k < nchunks ? reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k] : make_uint4(0u, 0u, 0u, 0u);
         mine = span_concat(mine, span_from_summary(sum[k]));
     }
-    // everything before this block: ordered reduction of the block aggregates 0 .. blk-1 (earlier windows included)
+    // everything before this block: ordered reduction of the block aggregates 0 .. blk-1
     SpanAcc before = span_empty();
     for (uint32_t b0 = 0; b0 < blk; b0 += 1024u) {
         const uint32_t j = b0 + threadIdx.x;

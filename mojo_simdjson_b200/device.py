@@ -56,7 +56,7 @@ class Stage1Context:
         if rc != errors.SUCCESS:
             raise ValueError("warps must be 0, 2, 4, 8, 16 or 24")
 
-    KERNELS = {"auto": 0, "persistent": 2, "split": 4, "stream": 5, "fused": 6}
+    KERNELS = {"auto": 0, "persistent": 2, "split": 4, "stream": 5}
 
     def reserve(self, length: int, stream_pipeline: bool = False) -> None:
         """Allocate the scratch for documents of up to `length` bytes now (otherwise: on first use, stream ordered)."""

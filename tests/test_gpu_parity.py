@@ -194,7 +194,7 @@ def test_adversarial_corpus_device(dev, scratch, warps):
 
 
 @pytest.mark.parametrize("kernel,warps", [("persistent", 2), ("persistent", 4), ("persistent", 8), ("persistent", 16), ("persistent", 24),
-                                          ("split", 8), ("split", 16), ("stream", 8), ("stream", 2), ("fused", 8), ("fused", 2)])
+                                          ("split", 8), ("split", 16), ("stream", 8), ("stream", 2)])
 def test_adversarial_corpus_every_kernel_organisation(dev, scratch, kernel, warps):
     """The same corpus through each kernel organisation (sjb200_ctx_set_kernel): results must not depend on it."""
     tiles = tuple(sorted({warps * 2048, 4096}))
@@ -221,7 +221,7 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
             head = b'["' + b"a" * lead
             data = head + b"\\" * 0 + b"\\"[:1] * run + b'"x", "y\\"", 1, {"k": "\\\\"}]' + b" " * 3000 + b"[]"
             want = oracle.stage1(data, impl="ref")
-            for kernel in ("stream", "fused", "persistent"):
+            for kernel in ("stream", "persistent"):
                 res, out = run_device(dev, scratch, data, kernel=kernel, warps=8)
                 try:
                     assert_same(res, out, want)
@@ -232,7 +232,7 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
     bad = b'["' + b"a" * 2046 + b"\\"[:1] * (2048 * 40 + 1) + b'" ]'   # 80 KiB + 1 backslashes ending on a chunk boundary
     walk = b'["' + b"a" * 2040 + b"\\"[:1] * 200 + b'" ]'               # resolved by the walk
     wok, wbad, wwalk = oracle.stage1(ok), oracle.stage1(bad, impl="fast"), oracle.stage1(walk)
-    for kernel in ("stream", "fused"):
+    for kernel in ("stream",):
         for _ in range(6):
             res, out = run_device(dev, scratch, ok, kernel=kernel)
             assert_same(res, out, wok)
@@ -244,7 +244,7 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
     data = b"\\"[:1] * 4095 + b'"' + b'"abc"' + b" " * 3000 + b"[1]"
     want = oracle.stage1(data, impl="ref")
     for mis in (0, 1, 7, 15):
-        for kernel in ("stream", "fused", "persistent"):
+        for kernel in ("stream", "persistent"):
             dev.set_kernel(kernel)
             dev.set_warps(8)
             scratch.inp[: mis + len(data) + 64].fill_(0x5C)
@@ -257,7 +257,7 @@ def test_stream_pipeline_speculation_and_fallback(dev, scratch):
             assert_same(res, scratch.out, want)
 
 
-@pytest.mark.parametrize("kernel", ["fused", "stream", "split", "persistent"])
+@pytest.mark.parametrize("kernel", ["stream", "split", "persistent"])
 def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
     """2 KiB chunks that contribute no index (inside a long string) at every 16-byte phase of the output cursor, and chunks
     that contribute 1, 2, 3 indexes: the flatten kernel's vector copy must not touch a neighbour's entries."""
@@ -286,7 +286,7 @@ def test_chunks_without_structurals_at_every_output_phase(dev, scratch, kernel):
         assert int((scratch.out[:shift] != -1).sum()) == 0
 
 
-@pytest.mark.parametrize("kernel", ["split", "stream", "fused"])
+@pytest.mark.parametrize("kernel", ["split", "stream"])
 def test_split_pair_capacity_and_flags(dev, scratch, kernel):
     data = b'[' + b'1,' * 40000 + b'1]'
     want = oracle.stage1(data, impl="fast")
@@ -348,7 +348,7 @@ def test_dense_tile_takes_direct_path(dev, scratch):
     for warps in (2, 8, 16, 24):
         res, out = run_device(dev, scratch, data, warps=warps)
         assert_same(res, out, want)
-    for kernel in ("fused", "stream", "split"):
+    for kernel in ("stream", "split"):
         res, out = run_device(dev, scratch, data, warps=8, kernel=kernel)
         assert_same(res, out, want)
 
@@ -375,9 +375,9 @@ def test_alternating_kernel_kinds_and_tile_shapes(dev, scratch):
     for warps in (2, 24, 2, 2, 24, 24, 2, 16, 4, 24, 8, 2, 24, 2):
         res, out = run_device(dev, scratch, a, warps=warps)
         assert_same(res, out, wa)
-    seq = [("split", 8), ("persistent", 2), ("fused", 2), ("split", 16), ("split", 8), ("fused", 8), ("fused", 8), ("split", 8),
-           ("persistent", 16), ("fused", 4), ("stream", 4), ("split", 16), ("stream", 8), ("stream", 8), ("fused", 2),
-           ("stream", 2), ("persistent", 2), ("stream", 16), ("split", 8), ("stream", 4), ("fused", 24), ("persistent", 24)]
+    seq = [("split", 8), ("persistent", 2), ("stream", 2), ("split", 16), ("split", 8), ("stream", 8), ("stream", 8), ("split", 8),
+           ("persistent", 16), ("stream", 4), ("stream", 4), ("split", 16), ("stream", 8), ("stream", 8), ("persistent", 4),
+           ("stream", 2), ("persistent", 2), ("stream", 16), ("split", 8), ("stream", 4), ("stream", 24), ("persistent", 24)]
     for kernel, warps in seq:
         res, out = run_device(dev, scratch, a, warps=warps, kernel=kernel)
         assert_same(res, out, wa)
@@ -413,7 +413,7 @@ def test_twitter_like_631k(dev):
         res = dev.index(inp, out)
         assert_same(res, out, want)
     dev.set_warps(0)
-    for kernel in ("fused", "stream", "split"):
+    for kernel in ("stream", "split"):
         dev.set_kernel(kernel)
         out.fill_(-1)
         res = dev.index(inp, out)
@@ -430,7 +430,7 @@ def test_document_64mib_full_compare(dev):
     assert want.error == 0
     inp = torch.from_numpy(doc).cuda()
     out = torch.empty(size // 3, dtype=torch.int32, device="cuda")
-    for kernel, warps in (("persistent", 2), ("persistent", 8), ("persistent", 16), ("persistent", 24), ("split", 0), ("stream", 0), ("fused", 0), ("auto", 0)):
+    for kernel, warps in (("persistent", 2), ("persistent", 8), ("persistent", 16), ("persistent", 24), ("split", 0), ("stream", 0), ("auto", 0)):
         dev.set_kernel(kernel)
         dev.set_warps(warps)
         out.fill_(-1)
@@ -659,7 +659,7 @@ def test_maximum_length_document(kernel):
         ctx.close()
 
 
-@pytest.mark.parametrize("kernel", ["fused", "stream", "persistent"])
+@pytest.mark.parametrize("kernel", ["stream", "persistent"])
 def test_utf8_verdicts_sparse_lanes(dev, scratch, kernel):
     """Valid and invalid UTF-8 sequences in otherwise ASCII documents, placed so that they straddle lane (64 B) and chunk
     (2 KiB) boundaries, sit at the very start / end of the document, or follow a lane that is pure ASCII: in the stream
@@ -759,7 +759,7 @@ def _heavy_only_cases():
     return [(n, d) for n, d in cases.adversarial_cases(tile_bytes=(4096, 8192, 16384), heavy=True) if n not in base]
 
 
-@pytest.mark.parametrize("kernel", ["fused", "stream", "split", "persistent"])
+@pytest.mark.parametrize("kernel", ["stream", "split", "persistent"])
 def test_adversarial_corpus_heavy(dev, scratch, kernel):
     """65535 / 65536 / 2^20+1 backslash runs at every offset and the larger fuzz set (cases.adversarial_cases(heavy=True))."""
     heavy = _heavy_only_cases()
@@ -781,7 +781,7 @@ def test_every_kernel_and_tile_shape_pair(dev, scratch):
 
     data = bytes(synth.status_array(300_000)) + b" " * 777
     want = oracle.stage1(data, impl="fast")
-    for kernel in ("auto", "persistent", "split", "stream", "fused"):
+    for kernel in ("auto", "persistent", "split", "stream"):
         for warps in (0, 2, 4, 8, 16, 24):
             res, out = run_device(dev, scratch, data, warps=warps, kernel=kernel)
             if kernel == "split" and warps in (2, 4, 24):
@@ -791,7 +791,7 @@ def test_every_kernel_and_tile_shape_pair(dev, scratch):
     for bad in (1, 3, 12, 32, 64):
         with pytest.raises(ValueError):
             dev.set_warps(bad)
-    for bad in (1, 3, 7):
+    for bad in (1, 3, 6, 7):
         with pytest.raises(ValueError):
             dev.set_kernel(bad)
 
