@@ -150,8 +150,7 @@ cudaError_t prepare_stream(int *occ) {
     using Cfg = StreamCfg<STREAM_NW>;
     // every kernel of the pipeline asks for the same shared-memory carve-out: kernels with different L1 / shared splits
     // cannot share an SM, and scan + flatten of one window must run beside the classify CTAs of the next
-    cudaFuncSetAttribute(stage1_span_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_span_carries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_span_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
@@ -192,7 +191,7 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
     return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
 }
-// The stream pipeline (stage1_stream.cuh): classify -> span_reduce -> span_carries -> flatten, stream ordered; the dependent
+// The stream pipeline (stage1_stream.cuh): classify -> span_scan -> flatten, stream ordered; the dependent
 // launches overlap their launch latency with their predecessor (programmatic dependent launch).
 template <bool UTF8>
 cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
@@ -205,11 +204,10 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, 0u, nchunks);
     cudaError_t e = cudaGetLastError();
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
-    if (e == cudaSuccess) e = launch_dependent(stage1_span_reduce_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
-    if (e == cudaSuccess) e = launch_dependent(stage1_span_carries_kernel, nblocks, 1024, 0, s, pdl, p, nchunks, 0u);
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess)
         e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
-    c->launches += 4;
+    c->launches += 3;
     return e;
 }
 
@@ -257,7 +255,8 @@ cudaError_t ensure_scratch(sjb200_ctx *c, uint64_t chunks, cudaStream_t s) {
     cudaError_t e = cudaMallocAsync(&c->d_masks, n * 512, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_carry, n * 8, s);
     if (e == cudaSuccess) e = cudaMallocAsync(&c->d_chunk_sum, n * 16, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 16, s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&c->d_block_sum, (n / SPAN_BLOCK + 2) * 32, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_block_sum, 0, (n / SPAN_BLOCK + 2) * 32, s);   // generation-tagged: no stale tag may match
     if (e != cudaSuccess) {
         free_scratch(c, s);
         cudaGetLastError();
@@ -287,6 +286,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
         cudaMemsetAsync(c->desc, 0, (size_t)c->max_tiles * 8, c->stream);
         cudaMemsetAsync(c->ticket, 0, 256, c->stream);
         cudaMemsetAsync(c->d_spec_flag, 0, 256, c->stream);
+        if (c->d_block_sum) cudaMemsetAsync(c->d_block_sum, 0, (c->scratch_chunks / SPAN_BLOCK + 2) * 32, c->stream);
         c->gen = 1;
     }
     p.gen = c->gen;

@@ -1,4 +1,4 @@
-// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of four stream-ordered launches with no
+// stage1_stream.cuh -- stage 1 of a large, device-resident document as a pipeline of three stream-ordered launches with no
 // waiting between warps, CTAs or launches other than stream order (and programmatic dependent launch between them):
 //
 //   stream_classify : every warp is its own pipeline.  A warp draws runs of 4 consecutive 2 KiB chunks from an atomic
@@ -8,9 +8,9 @@
 //                     chunk unknown -> one plane per parity) and a 16-byte summary {count0, count1, flags}.  At most 8
 //                     lanes per chunk with bytes >= 0x80 park their bit planes in the warp's shared-memory slots and are
 //                     validated 32 at a time at the end of the run (instead of one warp per lane).
-//   span_reduce     : 4096 chunk summaries per CTA -> one block aggregate (ordered, non-commutative span_concat).
-//   span_carries    : block prefix from the block aggregates, then the same local scan -> one carry word per chunk
-//                     (bit 63 = starts inside a string, bits 0..39 = rank of its first index) and the verdict.
+//   span_scan       : one CTA per 4096 chunk summaries: ordered (non-commutative span_concat) local reduction -> block
+//                     aggregate, published; the aggregates of the earlier blocks -> one carry word per chunk (bit 63 =
+//                     starts inside a string, bits 0..39 = rank of its first index) and the verdict.
 //   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
 //
 // The carries a 32-byte look-behind cannot decide are the escape state after a backslash run that covers all of it and the
@@ -105,6 +105,14 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
 // Reference: the carry `next_is_escaped` of json_escape_scanner.mojo:13,31, resolved without a serial dependency.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t WALK_MAX = 64u << 10;
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint4 ld_cg_u4(const void *p) {
     uint4 v;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -357,27 +365,16 @@ __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint
 constexpr int SPAN_PER_THREAD = 4;                         // consecutive chunk summaries per thread
 constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
 
-// blocks [block_begin, block_begin + gridDim.x) of SPAN_BLOCK chunk summaries each
-__global__ void __launch_bounds__(1024) stage1_span_reduce_kernel(const Stage1Params P, uint32_t nchunks, uint32_t block_begin) {
+// One launch, one CTA per SPAN_BLOCK chunk summaries (8 MiB of input): local ordered reduction -> the block aggregate,
+// published with a generation tag -> the aggregates of all earlier blocks (a CTA only ever waits for CTAs with a lower
+// block index, which are resident or finished: CTAs are dispatched in index order) -> one carry word per chunk; the
+// thread that owns the document's last chunk writes the verdict (finish(), reference json_structural_indexer.mojo:147-186).
+// block_sum: 32 bytes per block, {count0, count1, flags, 0} then {generation, 0, 0, 0}.
+__global__ void __launch_bounds__(1024) stage1_span_scan_kernel(const Stage1Params P, uint32_t nchunks) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
-    const uint32_t blk = block_begin + blockIdx.x;
-    const uint32_t c0 = blk * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
-    SpanAcc mine = span_empty();
-#pragma unroll
-    for (int k = 0; k < SPAN_PER_THREAD; k++)
-        if (c0 + k < nchunks) mine = span_concat(mine, span_from_summary(reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k]));
-    SpanAcc total;
-    block_span_inclusive(mine, s_w, total);
-    if (threadIdx.x == 0) reinterpret_cast<uint4 *>(P.block_sum)[blk] = make_uint4(total.c[0], total.c[1], span_flags(total), 0u);
-}
-
-__global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1Params P, uint32_t nchunks, uint32_t block_begin) {
-    __shared__ uint4 s_w[32];
-    grid_dependency_wait();
-    if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
-    const uint32_t blk = block_begin + blockIdx.x;
+    const uint32_t blk = blockIdx.x;
     const uint32_t c0 = blk * SPAN_BLOCK + threadIdx.x * SPAN_PER_THREAD;
     uint4 sum[SPAN_PER_THREAD];
     SpanAcc mine = span_empty();
@@ -386,17 +383,28 @@ __global__ void __launch_bounds__(1024) stage1_span_carries_kernel(const Stage1P
         sum[k] = c0 + k < nchunks ? reinterpret_cast<const uint4 *>(P.chunk_sum)[c0 + k] : make_uint4(0u, 0u, 0u, 0u);
         mine = span_concat(mine, span_from_summary(sum[k]));
     }
-    // everything before this block: ordered reduction of the block aggregates 0 .. blk-1
+    SpanAcc total;
+    const SpanAcc local = block_span_inclusive(mine, s_w, total);
+    uint4 *agg = reinterpret_cast<uint4 *>(P.block_sum);
+    if (threadIdx.x == 0 && blk + 1u < gridDim.x) {
+        agg[2 * blk] = make_uint4(total.c[0], total.c[1], span_flags(total), 0u);
+        __threadfence();
+        st_release_u32(P.block_sum + 8 * blk + 4, P.gen);
+    }
+    // everything before this block: ordered reduction of the block aggregates 0 .. blk-1 (1024 per round)
     SpanAcc before = span_empty();
     for (uint32_t b0 = 0; b0 < blk; b0 += 1024u) {
         const uint32_t j = b0 + threadIdx.x;
-        const SpanAcc bj = j < blk ? span_from_summary(reinterpret_cast<const uint4 *>(P.block_sum)[j]) : span_empty();
-        SpanAcc total;
-        block_span_inclusive(bj, s_w, total);
-        before = span_concat(before, total);
+        SpanAcc bj = span_empty();
+        if (j < blk) {
+            while (ld_acquire_u32(P.block_sum + 8 * j + 4) != P.gen) __nanosleep(100);
+            bj = span_from_summary(ld_cg_u4(agg + 2 * j));
+        }
+        SpanAcc round;
+        block_span_inclusive(bj, s_w, round);
+        before = span_concat(before, round);
     }
-    SpanAcc total;
-    const SpanAcc incl = span_concat(before, block_span_inclusive(mine, s_w, total));
+    const SpanAcc incl = span_concat(before, local);
     // the document starts outside a string: the state entering a chunk is the span before it evaluated at s = 0.
     // Walk this thread's chunks backwards from its inclusive span: before(k) = inclusive(k) "minus" chunk k.
     uint32_t par = incl.par & 1u, cnt = incl.c[0], un = incl.un[0], u8 = incl.u8;
