@@ -252,6 +252,28 @@ int32_t sjb200_batch_plan_resident(sjb200_batch *batch, int32_t local_gpu, const
 int32_t sjb200_batch_run_resident_async(sjb200_batch *batch, uint32_t *const *d_idx, const uint64_t *idx_capacities, uint32_t flags);
 int32_t sjb200_batch_finish(sjb200_batch *batch, int32_t *all_rows, int32_t *global_error);
 
+/*
+ * SURVEY.md section 8(f) rank 3, first slice -- the per-primitive half of stage 2 over the index array stage 1 left on the
+ * device.  For every structural k < n, as the reference's visit_primitive (generic/stage2/json_iterator.mojo:306-329)
+ * would treat the byte it points at:
+ *   kind[k]    0 structural character, 1 string, 2 integer, 3 float, 4 true, 5 false, 6 null, 7 anything else
+ *   err[k]     simdjson error code of that primitive: 0, STRING_ERROR 5 (parse_string, string_parsing.mojo:334-386),
+ *              T/F/N_ATOM_ERROR 6/7/8 (atom_parsing.mojo:34-80), NUMBER_ERROR 9 (number_parsing.mojo:22-80), TAPE_ERROR 3
+ *   value[k]   strings: unescaped length; integers: the value; floats: token length
+ *   str_off[k] strings: offset of the string's record in strbuf
+ *   strbuf     (may be NULL) every string unescaped, in index order, as the reference's string buffer holds it: uint32
+ *              length, then the bytes, no terminator (tape_builder.mojo:268-301); a string that fails gets length 0
+ *   summary    4 x uint64 on the device: [0] = (k << 8 | error) of the first failing primitive in index order, all ones if
+ *              none -- the error the sequential walk would have returned, grammar (TAPE / DEPTH) errors aside; [1] = bytes
+ *              of string records (what strbuf must hold; records that do not fit strbuf_capacity are not written)
+ * Stream ordered on the context's stream; nothing is copied to the host.  Semantics: oracle/stage2_oracle.c, whose header
+ * lists the two places where the reference cannot be restated as written (string scanner stride, standard-library number
+ * conversions).  Bytes at or beyond len read as 0x20.
+ */
+int32_t sjb200_stage2_primitives_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, const uint32_t *d_idx, uint64_t n,
+                                              uint8_t *d_kind, uint8_t *d_err, int64_t *d_value, uint64_t *d_str_off, uint8_t *d_strbuf,
+                                              uint64_t strbuf_capacity, uint64_t *d_summary);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,29 @@ class Stage1Context:
         self._depth_scratch = scratch  # keep it alive until the stream has used it
         return out
 
+    def stage2_primitives(self, buf: torch.Tensor, idx: torch.Tensor, n: int, want_strings: bool = True):
+        """The per-primitive half of stage 2 over a stage-1 index array (include/simdjson_b200.h,
+        sjb200_stage2_primitives_device_async).  Returns a dict of device tensors: kind, error (uint8 [n]), value (int64 [n]),
+        str_off (int64 [n]), string_buf (uint8, the reference's {uint32 length, bytes} records; None unless want_strings),
+        summary (int64 [4]: first failing primitive as k << 8 | error or -1, bytes of string records)."""
+        assert buf.is_cuda and buf.dtype == torch.uint8 and buf.is_contiguous()
+        assert idx.is_cuda and idx.element_size() == 4 and idx.is_contiguous() and idx.numel() >= n
+        dev = buf.device
+        kind = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        err = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        value = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        off = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        summary = torch.empty(4, dtype=torch.int64, device=dev)
+        # every unescaped string is no longer than its source, and every string costs at least its two quotes: len + 2 n bounds the records
+        cap = buf.numel() + 2 * n + 64 if want_strings else 0
+        sbuf = torch.empty(cap, dtype=torch.uint8, device=dev) if want_strings else None
+        rc = self._lib.sjb200_stage2_primitives_device_async(self._ctx, buf.data_ptr(), buf.numel(), idx.data_ptr(), n, kind.data_ptr(), err.data_ptr(),
+                                                             value.data_ptr(), off.data_ptr(), sbuf.data_ptr() if want_strings else None, cap,
+                                                             summary.data_ptr())
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"stage-2 primitives failed: {errors.NAMES.get(rc, rc)}")
+        return {"kind": kind[:n], "error": err[:n], "value": value[:n], "str_off": off[:n], "string_buf": sbuf, "summary": summary}
+
     def last_elapsed_ms(self) -> float:
         return float(self._lib.sjb200_last_elapsed_ms(self._ctx))
 

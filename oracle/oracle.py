@@ -213,3 +213,91 @@ def document_starts(structural_byte_values) -> np.ndarray:
     step[(b == ord("}")) | (b == ord("]"))] = -1
     before = np.cumsum(step) - step
     return (before == 0).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 2, per-primitive half (oracle/stage2_oracle.c): strings, atoms, numbers
+# ------------------------------------------------------------------------------------------------
+TAPE_ERROR, STRING_ERROR, T_ATOM_ERROR, F_ATOM_ERROR, N_ATOM_ERROR, NUMBER_ERROR = 3, 5, 6, 7, 8, 9
+KIND_NONE, KIND_STRING, KIND_INT, KIND_FLOAT, KIND_TRUE, KIND_FALSE, KIND_NULL, KIND_BAD = range(8)
+
+_stage2 = None
+
+
+def stage2_lib() -> C.CDLL:
+    global _stage2
+    if _stage2 is None:
+        path = os.path.join(_HERE, "liboracle_stage2.so")
+        src = os.path.join(_HERE, "stage2_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle_stage2.so"])
+        L = C.CDLL(path)
+        L.oracle_parse_string.restype = C.c_int64
+        L.oracle_parse_string.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+        for name in ("oracle_is_valid_true_atom", "oracle_is_valid_false_atom", "oracle_is_valid_null_atom"):
+            f = getattr(L, name)
+            f.restype = C.c_int32
+            f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.oracle_parse_number.restype = C.c_int32
+        L.oracle_parse_number.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
+        L.oracle_stage2_primitives.restype = C.c_int32
+        L.oracle_stage2_primitives.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        _stage2 = L
+    return _stage2
+
+
+def parse_string(data, start: int, advance: int = 8):
+    """parse_string of the reference (generic/stage2/string_parsing.mojo:334-386) on the bytes after an opening quote at
+    data[start - 1].  Returns (unescaped bytes or None on STRING_ERROR, index of the closing quote).  advance = 32 restates
+    BYTES_PROCESSED as written (see stage2_oracle.c); gaps it never copies stay zero, like the reference's zero-filled buffer."""
+    L = stage2_lib()
+    a = _as_u8(data)
+    dst = np.zeros(a.size + 128, dtype=np.uint8)
+    end = C.c_uint64(0)
+    n = L.oracle_parse_string(a.ctypes.data, a.size, start, dst.ctypes.data, advance, C.byref(end))
+    return (None, None) if n < 0 else (bytes(dst[:n]), int(end.value))
+
+
+def parse_number(data, start: int = 0):
+    """(error, is_float, integer value, token length) of number_parsing.mojo:22-80 at data[start]."""
+    L = stage2_lib()
+    a = _as_u8(data)
+    isf, iv, tl = C.c_int32(0), C.c_int64(0), C.c_uint32(0)
+    err = L.oracle_parse_number(a.ctypes.data, a.size, start, C.byref(isf), C.byref(iv), C.byref(tl))
+    return int(err), bool(isf.value), int(iv.value), int(tl.value)
+
+
+def atom_valid(data, start: int, which: str) -> bool:
+    L = stage2_lib()
+    a = _as_u8(data)
+    f = {"true": L.oracle_is_valid_true_atom, "false": L.oracle_is_valid_false_atom, "null": L.oracle_is_valid_null_atom}[which]
+    return bool(f(a.ctypes.data, a.size, start))
+
+
+@dataclass
+class Stage2Primitives:
+    kind: np.ndarray        # uint8 [n]   KIND_*
+    error: np.ndarray       # uint8 [n]   simdjson error code of that primitive (0 = fine)
+    value: np.ndarray       # int64 [n]   strings: unescaped length; integers: value; floats: token length
+    str_off: np.ndarray     # uint64 [n]  strings: offset of the record (uint32 length + bytes) in string_buf
+    string_buf: np.ndarray  # uint8
+    first_error_index: int  # n if none
+    first_error: int
+
+
+def stage2_primitives(data, indexes) -> Stage2Primitives:
+    """Every structural of a stage-1 index array as the reference's visit_primitive would treat it (stage2_oracle.c)."""
+    L = stage2_lib()
+    a = _as_u8(data)
+    idx = np.ascontiguousarray(indexes, dtype=np.uint32)
+    n = int(idx.size)
+    kind = np.zeros(max(n, 1), dtype=np.uint8)
+    err = np.zeros(max(n, 1), dtype=np.uint8)
+    val = np.zeros(max(n, 1), dtype=np.int64)
+    off = np.zeros(max(n, 1), dtype=np.uint64)
+    sbuf = np.zeros(a.size + 4 * n + 64, dtype=np.uint8)
+    slen, fei, fe = C.c_uint64(0), C.c_uint64(0), C.c_int32(0)
+    L.oracle_stage2_primitives(a.ctypes.data if a.size else None, a.size, idx.ctypes.data if n else None, n, kind.ctypes.data, err.ctypes.data,
+                               val.ctypes.data, off.ctypes.data, sbuf.ctypes.data, C.byref(slen), C.byref(fei), C.byref(fe))
+    return Stage2Primitives(kind[:n], err[:n], val[:n], off[:n], sbuf[: slen.value].copy(), int(fei.value), int(fe.value))

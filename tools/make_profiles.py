@@ -1,7 +1,10 @@
 """Turns a `ncu --set full` capture of one document pass and the ncu launch list of bench.py into the files under profiles/.
-usage: python tools/make_profiles.py <capture.ncu-rep> <launches.csv> <ms_per_pass_from_bench>"""
-import collections, csv, json, subprocess, sys
+usage: python tools/make_profiles.py <capture.ncu-rep> <launches.csv> <ms_per_pass_from_bench> [tag, default r2] [git sha of the profiled build]"""
+import collections, csv, json, os, subprocess, sys
 rep, launches, ms = sys.argv[1], sys.argv[2], sys.argv[3]
+tag = sys.argv[4] if len(sys.argv) > 4 else 'r2'
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sha = sys.argv[5] if len(sys.argv) > 5 else subprocess.run(['git', '-C', root, 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, rows = rows[0], rows[1], rows[2:]
@@ -39,25 +42,29 @@ for r in rows:
             if val >= 0.3:
                 stalls[h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')] = round(val, 2)
     d['stalled_warps_per_issue'] = stalls
-    res[name.split('(')[0].replace('void ', '')] = d
+    key = name.split('(')[0].replace('void ', '')
+    if key in res:   # several passes captured: keep the first launch of every kernel
+        continue
+    res[key] = d
 json.dump({'command': 'ncu --set full --clock-control none --import-source on -k regex:stage1_ python tools/quickbench.py 1024  (KERNELS=stream; 1 GiB synthetic document, one document pass)',
+           'git_sha': sha,
            'note': f'Times under ncu are cold-cache and serialised (no programmatic dependent launch overlap); the shares are what to compare with the bench ({ms} ms per pass).',
-           'kernels': res}, open('profiles/r1_stream_ncu_summary.json', 'w'), indent=1)
+           'kernels': res}, open(f'profiles/{tag}_stream_ncu_summary.json', 'w'), indent=1)
 tot = sum(d['duration_us'] for d in res.values())
 dram = sum(d['dram_read'] + d['dram_write'] for d in res.values())
 for k, d in res.items():
     print('%-45s %8.1f us %5.1f%%  dram %.3f GB alu %.1f issue %.1f l1 %.1f' % (k, d['duration_us'], 100 * d['duration_us'] / tot, (d['dram_read'] + d['dram_write']) / 1e9, d['alu_pipe_pct'], d['issue_pct'], d['l1tex_pct']))
 t = json.load(open('profiles/traffic.json'))
 alg = t['stream']['algorithmic_bytes_per_pass']
-t['stream'].update({'kernels': ' -> '.join(res.keys()), 'dram_bytes_per_pass': int(dram),
+t['stream'].update({'git_sha': sha, 'source': f'profiles/{tag}_stream_ncu_summary.json', 'kernels': ' -> '.join(res.keys()), 'dram_bytes_per_pass': int(dram),
                     'dram_bytes_by_kernel': {k: int(d['dram_read'] + d['dram_write']) for k, d in res.items()},
                     'kernel_shares': {k: round(d['duration_us'] / tot, 4) for k, d in res.items()},
-                    'note': 'traffic is %.2fx the algorithmic bytes: classify writes the two structural mask planes (16 B per 64 input bytes) and parks the bit planes of the lanes whose UTF-8 validation is deferred (80 B per such lane), flatten reads one mask plane back (8 B per 64); input read once, every index written once' % (dram / alg)})
+                    'note': 'traffic is %.2fx the algorithmic bytes: classify writes the two structural mask planes (16 B per 64 input bytes), flatten reads one mask plane back (8 B per 64); input read once, every index written once' % (dram / alg)})
 json.dump(t, open('profiles/traffic.json', 'w'), indent=1)
 print('total us', tot, 'dram', dram, 'x algorithmic', dram / alg)
 rows = list(csv.reader(open(launches)))
-with open('profiles/r1_stream_bench_launches.csv', 'w') as f:
-    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1\n')
+with open(f'profiles/{tag}_stream_bench_launches.csv', 'w') as f:
+    f.write(f'# git {sha}: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1\n')
     f.write('# (the 64 extra stage1_persistent_kernel launches belong to the chunked host path of the e2e leg; the short ones are the no-op fallback)\n')
     w = csv.writer(f)
     for r in rows:
