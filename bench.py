@@ -356,8 +356,8 @@ def kernel_kind_for(args, seg_bytes: int) -> str:
 
 
 KERNEL_NAMES = {
-    "stream": "stage-1 stream pipeline, 5 launches per document: stage1_stream_classify_kernel -> stage1_span_reduce_kernel -> "
-              "stage1_span_carries_kernel -> stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)",
+    "stream": "stage-1 stream pipeline, 4 launches per document: stage1_stream_classify_kernel -> stage1_span_scan_kernel -> "
+              "stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)",
     "persistent": "stage1_persistent_kernel", "split": "stage1_classify_kernel + stage1_flatten_kernel",
 }
 

@@ -243,6 +243,9 @@ def stage2_lib() -> C.CDLL:
         L.oracle_stage2_primitives.restype = C.c_int32
         L.oracle_stage2_primitives.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        L.oracle_stage2_walk.restype = C.c_int32
+        L.oracle_stage2_walk.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
+                                         C.POINTER(C.c_uint64)]
         _stage2 = L
     return _stage2
 
@@ -301,3 +304,74 @@ def stage2_primitives(data, indexes) -> Stage2Primitives:
     L.oracle_stage2_primitives(a.ctypes.data if a.size else None, a.size, idx.ctypes.data if n else None, n, kind.ctypes.data, err.ctypes.data,
                                val.ctypes.data, off.ctypes.data, sbuf.ctypes.data, C.byref(slen), C.byref(fei), C.byref(fe))
     return Stage2Primitives(kind[:n], err[:n], val[:n], off[:n], sbuf[: slen.value].copy(), int(fei.value), int(fe.value))
+
+
+DEPTH_ERROR = 4
+
+
+@dataclass
+class Stage2Tape:
+    error: int              # what walk_document returns (generic/stage2/json_iterator.mojo:40-254)
+    tape: np.ndarray        # uint64, the words appended until the walk returned
+    string_buf: np.ndarray  # uint8, {uint32 length, bytes} records in walk order
+
+
+def stage2_walk(data, indexes_with_trailer, n: int) -> Stage2Tape:
+    """The reference's stage-2 walk over a stage-1 result (indexes incl. the 3-entry trailer), restated in stage2_oracle.c."""
+    L = stage2_lib()
+    a = _as_u8(data)
+    idx = np.ascontiguousarray(indexes_with_trailer, dtype=np.uint32)
+    assert idx.size >= n + 3
+    tape = np.zeros(2 * n + 8, dtype=np.uint64)
+    sbuf = np.zeros(a.size + 4 * n + 64, dtype=np.uint8)
+    tl, sl = C.c_uint64(0), C.c_uint64(0)
+    err = L.oracle_stage2_walk(a.ctypes.data if a.size else None, a.size, idx.ctypes.data, n, tape.ctypes.data, tape.size, C.byref(tl), sbuf.ctypes.data,
+                               C.byref(sl))
+    return Stage2Tape(int(err), tape[: min(int(tl.value), tape.size)].copy(), sbuf[: sl.value].copy())
+
+
+def decode_tape(tape: np.ndarray, string_buf: np.ndarray):
+    """The document a tape describes, as python objects (objects as lists of (key, value) pairs so that order and duplicate keys
+    survive); checks the structure words on the way: start -> one past the matching end, end -> its start, counts, both roots."""
+    t = [int(x) for x in tape]
+    sb = bytes(string_buf)
+    N = len(t)
+    assert N >= 2 and t[0] >> 56 == ord("r") and (t[0] & ((1 << 56) - 1)) == N and t[N - 1] == ord("r") << 56
+
+    def string_at(off):
+        n = int.from_bytes(sb[off : off + 4], "little")
+        return sb[off + 4 : off + 4 + n].decode("utf-8", "surrogatepass")
+
+    def value(i):
+        w = t[i]
+        ty, payload = chr(w >> 56), w & ((1 << 56) - 1)
+        if ty == '"':
+            return string_at(payload), i + 1
+        if ty == "l":
+            v = t[i + 1]
+            return (v - (1 << 64) if v >> 63 else v), i + 2
+        if ty == "d":
+            return float(np.array([t[i + 1]], dtype=np.uint64).view(np.float64)[0]), i + 2
+        if ty in "tfn":
+            return {"t": True, "f": False, "n": None}[ty], i + 1
+        if ty in "[{":
+            end_next, count = payload & 0xFFFFFFFF, (payload >> 32) & 0xFFFFFF
+            close = "]" if ty == "[" else "}"
+            assert t[end_next - 1] >> 56 == ord(close) and (t[end_next - 1] & ((1 << 56) - 1)) == i
+            items, j = [], i + 1
+            while j < end_next - 1:
+                if ty == "{":
+                    k, j = value(j)
+                    assert isinstance(k, str)
+                    v, j = value(j)
+                    items.append((k, v))
+                else:
+                    v, j = value(j)
+                    items.append(v)
+            assert j == end_next - 1 and count == min(len(items), 0xFFFFFF)
+            return (items if ty == "[" else ("object", items)), end_next
+        raise AssertionError(f"unexpected tape word {w:#x} at {i}")
+
+    v, j = value(1)
+    assert j == N - 1
+    return v

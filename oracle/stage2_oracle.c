@@ -311,3 +311,304 @@ EXPORT int32_t oracle_stage2_primitives(const uint8_t *buf, uint64_t len, const 
 }
 
 EXPORT int32_t oracle_stage2_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The walk: JsonIterator.walk_document, generic/stage2/json_iterator.mojo:40-254, restated
+ * state for state -- the order of every check and therefore the error code it returns are the reference's.  What the walk
+ * APPENDS is the tape.  The reference's TapeBuilder is unfinished in three places, so the tape written here is the format
+ * its comments describe (upstream simdjson's), not what its code would leave in memory:
+ *   - end_container (tape_builder.mojo:227-254) announces "Write the ending tape element" but never appends one;
+ *   - next_tape_index (:206-208) is a difference of addresses, i.e. a BYTE offset, which start_container / end_container /
+ *     visit_document_end then use as an ELEMENT index (:216-225, :243-251, :100-108): every container start lands 8x too far;
+ *   - append_double (tape_writer.mojo:18-20) stores value.cast[uint64], a numeric conversion ("TODO: Is this type cast correct?").
+ * Tape words (64 bit, type character in the top byte, tape_type.mojo:1-13), element indexes:
+ *   tape[0] = 'r' | N            N = number of tape words (the final root included)
+ *   '{' / '[' | count << 32 | index of the word after the matching '}' / ']'     (count saturates at 0xFFFFFF upstream; the
+ *                                 reference returns CAPACITY above it, tape_builder.mojo:239-241, restated here)
+ *   '}' / ']' | index of the matching start
+ *   '"' | offset of the string's record in the string buffer
+ *   'l' | 0 followed by the int64 value; 'd' | 0 followed by the IEEE-754 bits (parity UNPINNED for doubles, see (2) above:
+ *                                 produced with strtod here and compared by the tests only where decimal -> binary is exact)
+ *   't' 'f' 'n' | 0
+ *   tape[N-1] = 'r' | 0
+ * PARITY: error codes pinned by code reading; the reference's tests only assert SUCCESS on four fixtures.  Tape UNPINNED.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <stdlib.h>
+
+enum { DEPTH_ERROR = 4, CAPACITY_ERROR = 1, EMPTY_ERROR = 13 };
+#define MAX_DEPTH 100 /* dom_parser_implementation.mojo:40: _max_depth = 100 */
+
+typedef struct {
+    const uint8_t *buf;
+    uint64_t len;
+    const uint32_t *idx;
+    uint64_t n, next; /* next structural */
+    uint64_t *tape;
+    uint64_t tape_cap, tape_len;
+    uint8_t *strbuf;
+    uint64_t str_len;
+} Walk;
+
+static inline void tape_append(Walk *w, uint64_t value, uint8_t type) {
+    if (w->tape && w->tape_len < w->tape_cap) w->tape[w->tape_len] = value | ((uint64_t)type << 56);
+    w->tape_len++;
+}
+static inline void tape_write(Walk *w, uint64_t at_index, uint64_t value, uint8_t type) {
+    if (w->tape && at_index < w->tape_cap) w->tape[at_index] = value | ((uint64_t)type << 56);
+}
+
+static int32_t walk_primitive(Walk *w, uint64_t i, int root) {
+    const uint8_t c = at(w->buf, w->len, i);
+    (void)root; /* the root forms differ only in how they guard reads past the end; bytes past the end read as 0x20 here */
+    if (c == '"') {
+        const uint64_t off = w->str_len;
+        int64_t l = oracle_parse_string(w->buf, w->len, i + 1, w->strbuf ? w->strbuf + off + 4 : 0, 8, 0);
+        if (l < 0) return STRING_ERROR;
+        tape_append(w, off, '"');
+        if (w->strbuf) {
+            const uint32_t l32 = (uint32_t)l;
+            memcpy(w->strbuf + off, &l32, 4);
+        }
+        w->str_len += 4 + (uint64_t)l;
+        return SUCCESS;
+    }
+    if (c == '-' || (c >= '0' && c <= '9')) { /* visit_primitive tests numbers before atoms (json_iterator.mojo:312-315) */
+        int32_t isf;
+        int64_t v;
+        uint32_t tl;
+        const int32_t e = oracle_parse_number(w->buf, w->len, i, &isf, &v, &tl);
+        if (e != SUCCESS) return e;
+        if (isf) {
+            char tmp[512];
+            double d = 0.0;
+            if (tl < sizeof tmp) {
+                for (uint32_t k = 0; k < tl; k++) tmp[k] = (char)at(w->buf, w->len, i + k);
+                tmp[tl] = 0;
+                d = strtod(tmp, 0);
+            }
+            uint64_t bits;
+            memcpy(&bits, &d, 8);
+            tape_append(w, 0, 'd');
+            tape_append(w, bits, 0);
+        } else {
+            tape_append(w, 0, 'l');
+            tape_append(w, (uint64_t)v, 0);
+        }
+        return SUCCESS;
+    }
+    if (c == 't') {
+        if (!oracle_is_valid_true_atom(w->buf, w->len, i)) return T_ATOM_ERROR;
+        tape_append(w, 0, 't');
+        return SUCCESS;
+    }
+    if (c == 'f') {
+        if (!oracle_is_valid_false_atom(w->buf, w->len, i)) return F_ATOM_ERROR;
+        tape_append(w, 0, 'f');
+        return SUCCESS;
+    }
+    if (c == 'n') {
+        if (!oracle_is_valid_null_atom(w->buf, w->len, i)) return N_ATOM_ERROR;
+        tape_append(w, 0, 'n');
+        return SUCCESS;
+    }
+    return TAPE_ERROR;
+}
+
+EXPORT int32_t oracle_stage2_walk(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint64_t n, uint64_t *tape, uint64_t tape_cap,
+                                  uint64_t *tape_len, uint8_t *strbuf, uint64_t *strbuf_len) {
+    Walk w = {buf, len, idx, n, 0, tape, tape_cap, 0, strbuf, 0};
+    uint32_t start_index[MAX_DEPTH + 2], count[MAX_DEPTH + 2];
+    uint8_t is_array[MAX_DEPTH + 2];
+    uint32_t depth = 0;
+    int32_t e;
+#define PEEK() at(buf, len, idx[w.next])   /* idx[n] = len: the trailer reads as padding */
+#define ADVANCE() (w.next < n + 2 ? idx[w.next++] : (uint32_t)len)
+#define FAIL(code)                 \
+    do {                           \
+        *tape_len = w.tape_len;    \
+        *strbuf_len = w.str_len;   \
+        return (code);             \
+    } while (0)
+    enum { DOC_START, OBJECT_BEGIN, OBJECT_FIELD, OBJECT_CONTINUE, SCOPE_END, ARRAY_BEGIN, ARRAY_VALUE, ARRAY_CONTINUE, DOC_END } state = DOC_START;
+    for (;;) {
+        switch (state) {
+        case DOC_START: {
+            if (w.next == n) FAIL(EMPTY_ERROR);                   /* at_eof (:45-46) */
+            start_index[0] = (uint32_t)w.tape_len;               /* visit_document_start: start_container at depth 0 */
+            count[0] = 0;
+            w.tape_len++;                                         /* skip: the root word is written at the end */
+            const uint32_t vi = ADVANCE();
+            const uint8_t v = at(buf, len, vi);
+            const uint8_t last = at(buf, len, idx[n - 1]);       /* last_structural (:283-291) */
+            if (v == '{' && last != '}') FAIL(TAPE_ERROR);
+            if (v == '[' && last != ']') FAIL(TAPE_ERROR);
+            if (v == '{') {
+                if (PEEK() == '}') {
+                    /* (the reference does not advance past the '}' here, :61-65; the final index check then fails) */
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '{');
+                    tape_append(&w, s, '}');
+                } else {
+                    state = OBJECT_BEGIN;
+                    continue;
+                }
+            } else if (v == '[') {
+                if (PEEK() == ']') {
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '[');
+                    tape_append(&w, s, ']');
+                } else {
+                    state = ARRAY_BEGIN;
+                    continue;
+                }
+            } else {
+                e = walk_primitive(&w, vi, 1);
+                if (e != SUCCESS) FAIL(e);
+            }
+            state = DOC_END;
+            continue;
+        }
+        case OBJECT_BEGIN: {
+            depth++;
+            if (depth > MAX_DEPTH) FAIL(DEPTH_ERROR);             /* :86-88: objects may reach depth == max_depth */
+            is_array[depth] = 0;
+            start_index[depth] = (uint32_t)w.tape_len;           /* visit_object_start */
+            count[depth] = 0;
+            w.tape_len++;
+            const uint32_t ki = ADVANCE();
+            if (at(buf, len, ki) != '"') FAIL(TAPE_ERROR);
+            count[depth]++;
+            e = walk_primitive(&w, ki, 0);                        /* visit_key = visit_string */
+            if (e != SUCCESS) FAIL(e);
+            state = OBJECT_FIELD;
+            continue;
+        }
+        case OBJECT_FIELD: {
+            if (at(buf, len, ADVANCE()) != ':') FAIL(TAPE_ERROR);
+            const uint32_t vi = ADVANCE();
+            const uint8_t v = at(buf, len, vi);
+            if (v == '{') {
+                if (PEEK() == '}') {
+                    (void)ADVANCE();
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '{');
+                    tape_append(&w, s, '}');
+                } else {
+                    state = OBJECT_BEGIN;
+                    continue;
+                }
+            } else if (v == '[') {
+                if (PEEK() == ']') {
+                    (void)ADVANCE();
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '[');
+                    tape_append(&w, s, ']');
+                } else {
+                    state = ARRAY_BEGIN;
+                    continue;
+                }
+            } else {
+                e = walk_primitive(&w, vi, 0);
+                if (e != SUCCESS) FAIL(e);
+            }
+            state = OBJECT_CONTINUE;
+            continue;
+        }
+        case OBJECT_CONTINUE: {
+            const uint8_t c = at(buf, len, ADVANCE());
+            if (c == ',') {
+                count[depth]++;
+                const uint32_t ki = ADVANCE();
+                if (at(buf, len, ki) != '"') FAIL(TAPE_ERROR);
+                e = walk_primitive(&w, ki, 0);
+                if (e != SUCCESS) FAIL(e);
+                state = OBJECT_FIELD;
+                continue;
+            } else if (c == '}') {
+                if (count[depth] > 0xFFFFFF) FAIL(CAPACITY_ERROR);
+                tape_append(&w, start_index[depth], '}');
+                tape_write(&w, start_index[depth], w.tape_len | ((uint64_t)count[depth] << 32), '{');
+                state = SCOPE_END;
+                continue;
+            }
+            FAIL(TAPE_ERROR);
+        }
+        case SCOPE_END: {
+            depth--;
+            if (depth == 0) {
+                state = DOC_END;
+                continue;
+            }
+            state = is_array[depth] ? ARRAY_CONTINUE : OBJECT_CONTINUE;
+            continue;
+        }
+        case ARRAY_BEGIN: {
+            depth++;
+            if (depth >= MAX_DEPTH) FAIL(DEPTH_ERROR);            /* :177-180: arrays fail one level earlier than objects */
+            is_array[depth] = 1;
+            start_index[depth] = (uint32_t)w.tape_len;
+            count[depth] = 0;
+            w.tape_len++;
+            count[depth]++;
+            state = ARRAY_VALUE;
+            continue;
+        }
+        case ARRAY_VALUE: {
+            const uint32_t vi = ADVANCE();
+            const uint8_t v = at(buf, len, vi);
+            if (v == '{') {
+                if (PEEK() == '}') {
+                    (void)ADVANCE();
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '{');
+                    tape_append(&w, s, '}');
+                } else {
+                    state = OBJECT_BEGIN;
+                    continue;
+                }
+            } else if (v == '[') {
+                if (PEEK() == ']') {
+                    (void)ADVANCE();
+                    const uint64_t s = w.tape_len;
+                    tape_append(&w, s + 2, '[');
+                    tape_append(&w, s, ']');
+                } else {
+                    state = ARRAY_BEGIN;
+                    continue;
+                }
+            } else {
+                e = walk_primitive(&w, vi, 0);
+                if (e != SUCCESS) FAIL(e);
+            }
+            state = ARRAY_CONTINUE;
+            continue;
+        }
+        case ARRAY_CONTINUE: {
+            const uint8_t c = at(buf, len, ADVANCE());
+            if (c == ',') {
+                count[depth]++;
+                state = ARRAY_VALUE;
+                continue;
+            } else if (c == ']') {
+                if (count[depth] > 0xFFFFFF) FAIL(CAPACITY_ERROR);
+                tape_append(&w, start_index[depth], ']');
+                tape_write(&w, start_index[depth], w.tape_len | ((uint64_t)count[depth] << 32), '[');
+                state = SCOPE_END;
+                continue;
+            }
+            FAIL(TAPE_ERROR);
+        }
+        case DOC_END: {
+            tape_append(&w, 0, 'r');                              /* visit_document_end (:96-108) */
+            tape_write(&w, 0, w.tape_len, 'r');
+            *tape_len = w.tape_len;
+            *strbuf_len = w.str_len;
+            if (w.next != n) return TAPE_ERROR;                   /* more than one value at the root / trailing content (:236-246) */
+            return SUCCESS;
+        }
+        }
+    }
+#undef PEEK
+#undef ADVANCE
+#undef FAIL
+}

@@ -85,13 +85,17 @@ int main(int argc, char **argv) {
     }
     printf("host batch: %d GPU(s), %u segments of ~%llu KiB, 3 passes bit-exact with the oracle, global verdict %d\n", G, nseg,
            (unsigned long long)(seg_bytes >> 10), worst);
-    // one broken segment (an extra quote in the last one): its verdict, the global verdict, and the others untouched
-    const uint64_t hit = seg_off[nseg - 1] + 10;
+    // one broken segment (the first quote of the last one blanked: it now ends inside a string): its verdict, the global
+    // verdict, and the others untouched
+    uint64_t hit = seg_off[nseg - 1];
+    while (buf[hit] != '"') hit++;
     const uint8_t saved = buf[hit];
-    buf[hit] = '"';
+    buf[hit] = ' ';
     rc = sjb200_batch_run(b, buf, size, idx, size + 3ull * max_total, seg_off.data(), seg_idx.data(), seg_n.data(), seg_err.data(), max_total, &nseg, &worst, 0);
     REQUIRE(rc == 0, "sjb200_batch_run (broken) -> %d", rc);
     if (check_segments(buf, idx, seg_off.data(), seg_idx.data(), seg_n.data(), seg_err.data(), nseg, worst)) return 1;
+    REQUIRE(seg_err[nseg - 1] != 0 && worst == seg_err[nseg - 1], "the broken segment must fail (got %d, global %d)", seg_err[nseg - 1], worst);
+    for (uint32_t s = 0; s + 1 < nseg; s++) REQUIRE(seg_err[s] == 0, "segment %u must be unaffected", s);
     printf("broken last segment: verdict %d on it, global verdict %d, the other %u segments unchanged\n", seg_err[nseg - 1], worst, nseg - 1);
     buf[hit] = saved;
 

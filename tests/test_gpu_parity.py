@@ -596,7 +596,7 @@ def nccl_library_path():
     try:
         import nvidia.nccl
 
-        p = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+        p = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2")
         return p if os.path.exists(p) else None
     except Exception:
         return None

@@ -202,3 +202,77 @@ def test_primitive_dispatch_and_first_error():
     errs = [int(e) for e, k in zip(p.error, p.kind) if k != oracle.KIND_NONE]
     assert errs == [0, oracle.F_ATOM_ERROR, oracle.STRING_ERROR, oracle.NUMBER_ERROR, oracle.N_ATOM_ERROR, 0, oracle.TAPE_ERROR, 0, 0]
     assert p.first_error == oracle.F_ATOM_ERROR and data[w.indexes[p.first_error_index] :].startswith(b"flase")
+
+
+# ------------------------------------------------------------------------------------------------
+# the walk: error codes of walk_document, and the tape against python's json
+# ------------------------------------------------------------------------------------------------
+def _as_pairs(obj):
+    """python's json result in the shape oracle.decode_tape returns (objects as ("object", [(k, v), ...]))."""
+    if isinstance(obj, list) and obj and isinstance(obj[0], tuple) and len(obj[0]) == 2 and obj[0][0] is _PAIR:
+        return ("object", [(k, _as_pairs(v)) for _, (k, v) in obj])
+    if isinstance(obj, _EmptyObject):
+        return ("object", [])
+    if isinstance(obj, list):
+        return [_as_pairs(v) for v in obj]
+    return obj
+
+
+class _EmptyObject:
+    pass
+
+
+def python_document(data: bytes):
+    parsed = json.loads(data.decode("utf-8"), object_pairs_hook=lambda pairs: [(_PAIR, p) for p in pairs] if pairs else _EmptyObject())
+    return _as_pairs(parsed)
+
+
+def walk(data: bytes):
+    w = oracle.stage1(data, impl="fast" if len(data) > 20000 else "ref")
+    assert w.error == 0, data[:60]
+    return oracle.stage2_walk(data, w.indexes, w.n)
+
+
+def same_document(a, b):
+    """Equal up to float formatting: python parses floats exactly, the oracle with strtod -- both correctly rounded."""
+    return a == b
+
+
+def test_walk_tape_decodes_to_what_python_parses():
+    from mojo_simdjson_b200 import synth
+
+    docs = [b'[1, 2]', b'{ " hello " : " world " }', b'{"a": {"b": [1, 2, {"c": null}], "d": "x"}, "e": [[], {}, [[]], true, false, -7, 2.5e3]}',
+            b'[[[[[[]]]]], {"k": {}}]', b'"just a string"', b"12345", b"-0", b"true", b"null", b'{"a":1,"a":2}',
+            bytes(synth.twitter_like()), bytes(synth.status_array(200_000))]
+    for data in docs:
+        t = walk(data)
+        assert t.error == 0, data[:60]
+        assert same_document(oracle.decode_tape(t.tape, t.string_buf), python_document(data)), data[:60]
+    for name, data in _fixture_inputs().items():   # what tests/test_stage_2.mojo asserts: error code 0
+        assert walk(data).error == 0, name
+
+
+def test_walk_error_codes():
+    """Derived by hand from json_iterator.mojo:40-254 (state by state); includes the reference's own oddities: a root-level
+    empty container is not consumed (:61-65, :72-76), so `{}` and `[]` end in TAPE_ERROR; arrays hit DEPTH_ERROR one level
+    before objects (:177-180 vs :86-88)."""
+    T, D = oracle.TAPE_ERROR, oracle.DEPTH_ERROR
+    table = {
+        b"{}": T, b"[]": T, b"[1]": 0, b'{"a":1}': 0, b"[1,]": T, b"[,1]": T, b"[1 2]": T, b'{"a" 1}': T, b'{"a":}': T, b"{1:2}": T, b'{"a":1,}': T,
+        b'{"a":1 "b":2}': T, b"[1}": T, b'{"a":1]': T, b"[1] 2": T, b"1 2": T, b'"a" "b"': T, b"[[1]": T, b"[1]]": T, b'{"a":[}': T,
+        b"[1,2": T, b'{"a":1': T, b"@": T, b"[@]": T, b"[tru]": oracle.T_ATOM_ERROR, b"[fals]": oracle.F_ATOM_ERROR, b"[nul]": oracle.N_ATOM_ERROR,
+        b"[12x]": oracle.NUMBER_ERROR, b'["\\q"]': oracle.STRING_ERROR, b'{"\\q":1}': oracle.STRING_ERROR, b"[1, tru, 12x]": oracle.T_ATOM_ERROR,
+        b"[12x, tru]": oracle.NUMBER_ERROR, b"[12x 3]": oracle.NUMBER_ERROR, b"[1 12x]": T, b"tru": oracle.T_ATOM_ERROR, b"-": oracle.NUMBER_ERROR,
+        b'[{"a":[1,{"b":[]}]}]': 0, b"[[],[]]": 0, b"[{},{}]": 0, b'{"a":{},"b":[]}': 0, b"[1,[2,[3]],4]": 0, b'{"a":"b","c":"d"}': 0,
+        b":": T, b",": T, b"]": T, b"}": T, b"[:]": T, b'{"a"::1}': T, b'{"a":1,,"b":2}': T, b"[1,,2]": T, b'[{"a":1},]': T,
+    }
+    for data, want in table.items():
+        assert walk(data).error == want, (data, walk(data).error, want)
+    # depth: arrays fail at depth 100, objects at depth 101
+    for depth, want in ((98, 0), (99, 0), (100, D), (101, D)):
+        assert walk(b"[" * depth + b"1" + b"]" * depth).error == want, depth
+    for depth, want in ((99, 0), (100, 0), (101, D), (102, D)):
+        assert walk(b'{"k":' * depth + b"1" + b"}" * depth).error == want, depth
+    # mixed: 99 arrays, then an object at depth 100 is fine, an array is not
+    assert walk(b"[" * 99 + b'{"k":1}' + b"]" * 99).error == 0
+    assert walk(b"[" * 99 + b"[1]" + b"]" * 99).error == D
