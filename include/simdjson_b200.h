@@ -274,6 +274,25 @@ int32_t sjb200_stage2_primitives_device_async(sjb200_ctx *ctx, const uint8_t *d_
                                               uint8_t *d_kind, uint8_t *d_err, int64_t *d_value, uint64_t *d_str_off, uint8_t *d_strbuf,
                                               uint64_t strbuf_capacity, uint64_t *d_summary);
 
+/*
+ * SURVEY.md section 8(f) rank 4, first slice -- the stage-2 walk: the verdict JsonIterator.walk_document would return
+ * (generic/stage2/json_iterator.mojo:40-254, restated in oracle/stage2_oracle.c: oracle_stage2_walk) and the tape, computed
+ * in parallel over the index array (d_idx holds n indexes; the trailer is not read).  d_kind / d_err / d_value / d_str_off are
+ * the outputs of sjb200_stage2_primitives_device_async for the same document.
+ *   tape     64-bit words, type character in the top byte (include/internal/tape_type.mojo): 'r' | N ... 'r' | 0 roots,
+ *            '{' '[' | count << 32 | index after the matching close, '}' ']' | index of the matching open, '"' | offset of
+ *            the string record, 'l' | 0 + int64, 'd' | 0 + IEEE-754 bits, 't' 'f' 'n' | 0; at most 2 n + 2 words
+ *   summary  4 x uint64 on the device: [0] all ones = SUCCESS, else index << 16 | check << 8 | error code of the first failing
+ *            token (TAPE_ERROR 3, DEPTH_ERROR 4 -- depth limit 100, dom_parser_implementation.mojo:40 --, the primitive's own
+ *            code, CAPACITY 1 for a container of more than 0xFFFFFF elements); [1] words appended by the tokens; [2] N;
+ *            [3] doubles whose bits are not guaranteed exact (outside the exact fast path: > 15 digits or |exponent| > 22)
+ * The tape is meaningful only when [0] says SUCCESS.  EMPTY if n == 0.  Tape parity with the reference is UNPINNED: its own
+ * tape_builder is unfinished (see the oracle's header); the format is the one its comments describe.
+ */
+int32_t sjb200_stage2_tape_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, uint64_t len, const uint32_t *d_idx, uint64_t n,
+                                        const uint8_t *d_kind, const uint8_t *d_err, const int64_t *d_value, const uint64_t *d_str_off,
+                                        uint64_t *d_tape, uint64_t tape_capacity, uint64_t *d_summary);
+
 #ifdef __cplusplus
 }
 #endif

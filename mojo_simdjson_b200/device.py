@@ -151,6 +151,20 @@ class Stage1Context:
             raise RuntimeError(f"stage-2 primitives failed: {errors.NAMES.get(rc, rc)}")
         return {"kind": kind[:n], "error": err[:n], "value": value[:n], "str_off": off[:n], "string_buf": sbuf, "summary": summary}
 
+    def stage2_tape(self, buf: torch.Tensor, idx: torch.Tensor, n: int, prims: dict):
+        """The stage-2 walk over a stage-1 index array: verdict + tape (include/simdjson_b200.h, sjb200_stage2_tape_device_async).
+        `prims` = the result of stage2_primitives for the same document.  Returns (tape int64 [2 n + 2] on the device, summary
+        int64 [4] on the device: first error or -1, token words, tape length, inexact doubles)."""
+        dev = buf.device
+        tape = torch.zeros(2 * n + 2, dtype=torch.int64, device=dev)
+        summary = torch.empty(4, dtype=torch.int64, device=dev)
+        rc = self._lib.sjb200_stage2_tape_device_async(self._ctx, buf.data_ptr(), buf.numel(), idx.data_ptr(), n, prims["kind"].data_ptr(),
+                                                       prims["error"].data_ptr(), prims["value"].data_ptr(), prims["str_off"].data_ptr(), tape.data_ptr(),
+                                                       tape.numel(), summary.data_ptr())
+        if rc != errors.SUCCESS:
+            raise RuntimeError(f"stage-2 tape failed: {errors.NAMES.get(rc, rc)}")
+        return tape, summary
+
     def last_elapsed_ms(self) -> float:
         return float(self._lib.sjb200_last_elapsed_ms(self._ctx))
 

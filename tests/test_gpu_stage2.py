@@ -133,3 +133,104 @@ def test_empty_index_array(dev):
     got = dev.stage2_primitives(d_in, d_idx, 0)
     torch.cuda.synchronize()
     assert got["summary"].cpu().tolist()[:2] == [-1, 0]
+
+
+# ------------------------------------------------------------------------------------------------
+# the walk: verdict of walk_document and the tape, against oracle_stage2_walk and python's json
+# ------------------------------------------------------------------------------------------------
+def run_walk(dev, data: bytes, mis: int = 0):
+    a = np.frombuffer(data, dtype=np.uint8)
+    store = torch.full((mis + a.size + 64,), 0x22, dtype=torch.uint8, device="cuda")
+    d_in = store[mis : mis + a.size]
+    d_in.copy_(torch.from_numpy(a.copy()))
+    d_idx = torch.empty(a.size + 8, dtype=torch.int32, device="cuda")
+    res = dev.index(d_in, d_idx)
+    w = oracle.stage1(data, impl="fast" if a.size > 20000 else "ref")
+    assert res.error == w.error == 0 and res.n == w.n, data[:60]
+    want = oracle.stage2_walk(data, w.indexes, w.n)
+    prims = dev.stage2_primitives(d_in, d_idx, res.n)
+    tape, summary = dev.stage2_tape(d_in, d_idx, res.n, prims)
+    torch.cuda.synchronize()
+    s = summary.cpu().numpy()
+    got_err = 0 if s[0] == -1 else int(s[0]) & 0xFF
+    assert got_err == want.error, (data[:80], got_err, want.error, int(s[0]) >> 16)
+    if want.error == 0:
+        assert int(s[2]) == want.tape.size
+        got = tape[: want.tape.size].cpu().numpy().view(np.uint64)
+        if int(s[3]) == 0:
+            assert np.array_equal(got, want.tape), data[:80]
+        else:   # some double lies outside the exact fast path: compare everything but the payload words of doubles
+            is_d = (want.tape >> np.uint64(56)) == np.uint64(ord("d"))
+            payload = np.zeros(want.tape.size, dtype=bool)
+            payload[1:] = is_d[:-1]
+            assert np.array_equal(got[~payload], want.tape[~payload]), data[:80]
+        assert np.array_equal(prims["string_buf"][: want.string_buf.size].cpu().numpy(), want.string_buf)
+        return got, prims["string_buf"][: want.string_buf.size].cpu().numpy(), int(s[3])
+    return None, None, 0
+
+
+def test_walk_error_codes_on_the_gpu(dev):
+    T, D = oracle.TAPE_ERROR, oracle.DEPTH_ERROR
+    docs = [b"{}", b"[]", b"[1]", b'{"a":1}', b"[1,]", b"[,1]", b"[1 2]", b'{"a" 1}', b'{"a":}', b"{1:2}", b'{"a":1,}', b'{"a":1 "b":2}', b"[1}", b'{"a":1]',
+            b"[1] 2", b"1 2", b'"a" "b"', b"[[1]", b"[1]]", b'{"a":[}', b"[1,2", b'{"a":1', b"@", b"[@]", b"[tru]", b"[fals]", b"[nul]", b"[12x]", b'["\\q"]',
+            b'{"\\q":1}', b"[1, tru, 12x]", b"[12x, tru]", b"[12x 3]", b"[1 12x]", b"tru", b"-", b'[{"a":[1,{"b":[]}]}]', b"[[],[]]", b"[{},{}]",
+            b'{"a":{},"b":[]}', b"[1,[2,[3]],4]", b'{"a":"b","c":"d"}', b":", b",", b"]", b"}", b"[:]", b'{"a"::1}', b'{"a":1,,"b":2}', b"[1,,2]",
+            b'[{"a":1},]', b"{} }", b"[] ]", b'[{"a" "b"}]', b'{"a":{"b":1 2}}', b'[[1,2],[3 4]]', b'{"a":[1,2,{"b":]}]}', b'[1,{"a":1,"b"}]',
+            b'["a":1]', b'{"a":1:2}', b"[[[[]]]]", b"[[[[]]]", b'[{"a":[{"b":[{"c":{}}]}]}]']
+    for data in docs:
+        run_walk(dev, data, mis=len(data) % 4)
+    for depth in (98, 99, 100, 101, 130, 300):
+        run_walk(dev, b"[" * depth + b"1" + b"]" * depth)
+        run_walk(dev, b'{"k":' * depth + b"1" + b"}" * depth)
+    run_walk(dev, b"[" * 99 + b'{"k":1}' + b"]" * 99)
+    run_walk(dev, b"[" * 99 + b"[1]" + b"]" * 99)
+    run_walk(dev, b"[" * 99 + b"[]" + b"]" * 99)      # an empty container does not count as a level
+
+
+def test_walk_tapes_against_the_oracle_and_python(dev):
+    from mojo_simdjson_b200 import synth
+
+    docs = [b"[1, 2]", b'{ " hello " : " world " }', b'{"a": {"b": [1, 2, {"c": null}], "d": "x"}, "e": [[], {}, [[]], true, false, -7, 2.5e3]}',
+            b'[[[[[[]]]]], {"k": {}}]', b'"just a string"', b"12345", b"-0", b"true", b"null", b'{"a":1,"a":2}', b"[0.1, 1e22, 123456789012345678, 1.5e-7, -2.25]",
+            bytes(synth.twitter_like()), bytes(synth.status_array(3 << 20))]
+    for data in docs:
+        tape, sbuf, inexact = run_walk(dev, data)
+        assert tape is not None, data[:60]
+        if inexact == 0:
+            assert oracle.decode_tape(tape, sbuf) == cpu.python_document(data), data[:60]
+    for name, data in cpu._fixture_inputs().items():
+        tape, _, _ = run_walk(dev, data)
+        assert tape is not None, name        # tests/test_stage_2.mojo: error code 0
+    # doubles outside the exact fast path are counted, never silently approximated
+    _, _, inexact = run_walk(dev, b"[0.1234567890123456789, 1e300, 3.5]")
+    assert inexact == 2
+
+
+def test_walk_fuzz(dev):
+    """Random token soups around valid documents: the GPU verdict must be the sequential walk's on every one of them."""
+    import random
+
+    rng = random.Random(7)
+    atoms = ['1', '-2', '3.5', 'true', 'false', 'null', '"s"', '"k"', '12x', 'tru', '"\\\\q"', '{}', '[]']
+
+    def gen(depth):
+        r = rng.random()
+        if depth > 4 or r < 0.35:
+            return rng.choice(atoms)
+        if r < 0.7:
+            return "[" + ",".join(gen(depth + 1) for _ in range(rng.randrange(0, 5))) + "]"
+        return "{" + ",".join('"k%d":%s' % (i, gen(depth + 1)) for i in range(rng.randrange(0, 4))) + "}"
+
+    mut = [",", ":", "[", "]", "{", "}", '"x"', "1", " ", ""]
+    done = 0
+    while done < 500:
+        s = gen(0)
+        for _ in range(rng.randrange(0, 3)):
+            p = rng.randrange(0, len(s) + 1)
+            s = s[:p] + rng.choice(mut) + s[p + rng.randrange(0, 2):]
+        data = s.encode()
+        w = oracle.stage1(data)
+        if w.error != 0 or not w.n:
+            continue
+        run_walk(dev, data)
+        done += 1
