@@ -293,6 +293,17 @@ int32_t sjb200_stage2_tape_device_async(sjb200_ctx *ctx, const uint8_t *d_buf, u
                                         const uint8_t *d_kind, const uint8_t *d_err, const int64_t *d_value, const uint64_t *d_str_off,
                                         uint64_t *d_tape, uint64_t tape_capacity, uint64_t *d_summary);
 
+/*
+ * Host-to-host stage 2: replaces DomParserImplementation.stage2 (include/generic/dom_parser_implementation.mojo:71-83, which
+ * sizes the document's tape and string buffer and calls TapeBuilder.parse_document).  Walks the document that the preceding,
+ * successful sjb200_stage1 call on this context left resident on the device -- primitives, then the walk -- and copies the
+ * tape (<= 2 n + 2 words) and the string buffer (<= len + 2 n bytes) back.  Returns the walk's verdict (SUCCESS, TAPE_ERROR,
+ * DEPTH_ERROR, STRING_ERROR, T/F/N_ATOM_ERROR, NUMBER_ERROR, CAPACITY); UNINITIALIZED without such a stage-1 call; CAPACITY
+ * also when an output does not fit.  On an error verdict the outputs are not written.  Synchronous.
+ */
+int32_t sjb200_stage2(sjb200_ctx *ctx, uint64_t *tape_out, uint64_t tape_capacity, uint8_t *strbuf_out, uint64_t strbuf_capacity,
+                      uint64_t *tape_len, uint64_t *strbuf_len, uint64_t *inexact_doubles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ SIGNATURES = {
     "sjb200_batch_plan_resident": (_i32, [_vp, _i32, _vp, _u64, _pu64, _pu64, _pu32]),
     "sjb200_batch_run_resident_async": (_i32, [_vp, C.POINTER(_vp), _pu64, _u32]),
     "sjb200_batch_finish": (_i32, [_vp, _pi32, _pi32]),
+    "sjb200_stage2": (_i32, [_vp, _vp, _u64, _vp, _u64, _pu64, _pu64, _pu64]),
     "sjb200_stage2_tape_device_async": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "sjb200_stage2_primitives_device_async": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
 }

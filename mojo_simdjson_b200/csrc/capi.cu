@@ -108,6 +108,9 @@ struct sjb200_ctx {
     uint64_t *d_split = nullptr;        // scratch for batch_split_device
     uint64_t *d_trace = nullptr;        // debug builds only
     uint32_t launch_seq = 0;            // alternates the persistent kernel's ticket counters
+    cudaMemPool_t pool = nullptr;       // stream-ordered pool of the stage-2 temporaries; keeps its memory between calls
+    uint64_t resident_len = 0;          // host path: the document of the last successful sjb200_stage1 is still in d_in / d_out
+    uint32_t resident_n = 0;
     // streaming host path: second stream for the device-to-host copies, one event + one mapped progress word per chunk
     cudaStream_t copy_stream = nullptr;
     static constexpr int MAX_CHUNKS = 256;
@@ -630,6 +633,18 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
     if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
     if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
+    if (e == cudaSuccess) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        e = cudaMemPoolCreate(&c->pool, &props);
+        if (e == cudaSuccess) {
+            uint64_t keep = ~0ull;   // freed blocks stay in the pool: a second call of the same size allocates nothing
+            e = cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->d_spec_flag, 256);
     if (e == cudaSuccess) e = cudaMemset(c->d_spec_flag, 0, 256);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -798,6 +813,9 @@ int32_t sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, uint64_t len, uint32_t 
     const Stage1Result r = c->h_results[c->slot];
     if (r.n_valid && n_out) *n_out = r.n;
     if (utf8_err_out) *utf8_err_out = (flags & SJB200_FLAG_NO_UTF8) ? -1 : r.utf8_error;
+    // the document and its index array stay resident: sjb200_stage2 walks them without another copy
+    c->resident_len = (r.error == SJB200_SUCCESS || r.error == SJB200_UTF8_ERROR) && r.n_valid ? len : 0;
+    c->resident_n = c->resident_len ? r.n : 0;
     return r.error;
 }
 

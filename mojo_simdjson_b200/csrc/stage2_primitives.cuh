@@ -342,7 +342,7 @@ int32_t sjb200_stage2_primitives_device_async(sjb200_ctx *c, const uint8_t *d_bu
     CK(cudaGetLastError());
     const uint64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     uint64_t *d_totals = nullptr;
-    CK(cudaMallocAsync(&d_totals, nblocks * 8, s));
+    CK(cudaMallocFromPoolAsync(&d_totals, nblocks * 8, c->pool, s));
     scan_totals_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(d_str_off, n, d_totals);
     scan_of_totals_kernel<<<1, 1024, 0, s>>>(d_totals, (uint32_t)nblocks, reinterpret_cast<unsigned long long *>(d_summary + 1));
     scan_apply_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(d_str_off, n, d_totals);

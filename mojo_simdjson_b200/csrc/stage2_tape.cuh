@@ -493,10 +493,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan32_apply_kernel(uint32_t *__
     }
 }
 // exclusive scan of x[0 .. n) in place on stream s; *d_total (device) receives the grand total
-cudaError_t scan32_exclusive(uint32_t *x, uint64_t n, unsigned long long *d_total, cudaStream_t s) {
+cudaError_t scan32_exclusive(uint32_t *x, uint64_t n, unsigned long long *d_total, cudaMemPool_t pool, cudaStream_t s) {
     const uint64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     uint64_t *d_totals = nullptr;
-    cudaError_t e = cudaMallocAsync(&d_totals, nblocks * 8, s);
+    cudaError_t e = cudaMallocFromPoolAsync(&d_totals, nblocks * 8, pool, s);
     if (e != cudaSuccess) return e;
     scan32_totals_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(x, n, d_totals);
     scan_of_totals_kernel<<<1, 1024, 0, s>>>(d_totals, (uint32_t)nblocks, d_total);
@@ -531,14 +531,14 @@ int32_t sjb200_stage2_tape_device_async(sjb200_ctx *c, const uint8_t *d_buf, uin
     uint32_t *d_words = nullptr, *d_slot = nullptr, *d_rank = nullptr, *d_sorted = nullptr, *d_hist = nullptr;
     uint8_t *d_cls = nullptr;
     unsigned long long *d_tot = nullptr;
-    cudaError_t e = cudaMallocAsync(&d_stk, nblk * sizeof(Stk), s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_words, n * 4, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_cls, n, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_slot, n * 4, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_rank, n * 4, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_sorted, n * 4, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_hist, hist_entries * 4, s);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_tot, 32, s);
+    cudaError_t e = cudaMallocFromPoolAsync(&d_stk, nblk * sizeof(Stk), c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_words, n * 4, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_cls, n, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_slot, n * 4, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_rank, n * 4, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_sorted, n * 4, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_hist, hist_entries * 4, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_tot, 32, c->pool, s);
     auto release = [&]() {
         if (d_stk) cudaFreeAsync(d_stk, s);
         if (d_words) cudaFreeAsync(d_words, s);
@@ -559,13 +559,13 @@ int32_t sjb200_stage2_tape_device_async(sjb200_ctx *c, const uint8_t *d_buf, uin
     tape_stack_scan_kernel<<<1, 1024, 0, s>>>(d_stk, (uint32_t)nblk);
     tape_grammar_kernel<<<(unsigned)nblk, TAPE_THREADS, 0, s>>>(d_buf, len, d_idx, n, d_kind, d_err, d_stk, d_words, d_cls, summary);
     // where every token's words go
-    e = scan32_exclusive(d_words, n, summary + 1, s);
+    e = scan32_exclusive(d_words, n, summary + 1, c->pool, s);
     // brackets and commas by depth: two class-major histograms, each scanned on its own, then the ranks
     if (e == cudaSuccess) {
         tape_multisplit_hist_kernel<<<ntiles, 32, 0, s>>>(d_cls, n, ntiles, d_hist);
-        e = scan32_exclusive(d_hist, (uint64_t)MS_CLASSES * ntiles, d_tot, s);                                     // B: total = number of brackets
+        e = scan32_exclusive(d_hist, (uint64_t)MS_CLASSES * ntiles, d_tot, c->pool, s);                                     // B: total = number of brackets
     }
-    if (e == cudaSuccess) e = scan32_exclusive(d_hist + (size_t)MS_CLASSES * ntiles, (uint64_t)MS_CLASSES * ntiles, d_tot + 1, s);   // A
+    if (e == cudaSuccess) e = scan32_exclusive(d_hist + (size_t)MS_CLASSES * ntiles, (uint64_t)MS_CLASSES * ntiles, d_tot + 1, c->pool, s);   // A
     uint32_t nbrackets_upper = (uint32_t)(n < 0xFFFFFFFFull ? n : 0xFFFFFFFFull);
     if (e == cudaSuccess) {
         tape_multisplit_rank_kernel<<<ntiles, 32, 0, s>>>(d_cls, n, ntiles, d_hist, 0u, d_slot, d_rank, d_sorted);
@@ -578,6 +578,67 @@ int32_t sjb200_stage2_tape_device_async(sjb200_ctx *c, const uint8_t *d_buf, uin
     release();
     c->launches += 14;
     return e == cudaSuccess ? SJB200_SUCCESS : cuda_err(e);
+}
+
+// Host-to-host stage 2, the drop-in for DomParserImplementation.stage2 (include/generic/dom_parser_implementation.mojo:71-83):
+// walks the document the preceding sjb200_stage1 call on this context left on the device (no second copy of the input),
+// copies the tape and the string buffer back.  Returns the walk's verdict.
+int32_t sjb200_stage2(sjb200_ctx *c, uint64_t *tape_out, uint64_t tape_capacity, uint8_t *strbuf_out, uint64_t strbuf_capacity, uint64_t *tape_len,
+                      uint64_t *strbuf_len, uint64_t *inexact_doubles) {
+    if (!c || !tape_out || !strbuf_out) return SJB200_UNINITIALIZED;
+    if (c->resident_len == 0 || c->resident_n == 0) return SJB200_UNINITIALIZED;   // no successful stage 1 before this call
+    const uint64_t len = c->resident_len, n = c->resident_n;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint64_t sb_cap = len + 2 * n + 64, tp_cap = 2 * n + 2;
+    uint8_t *d_kind = nullptr, *d_err = nullptr, *d_sb = nullptr;
+    int64_t *d_val = nullptr;
+    uint64_t *d_off = nullptr, *d_tape = nullptr, *d_sum = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync(&d_kind, n, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_err, n, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_val, n * 8, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_off, n * 8, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_sb, sb_cap, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_tape, tp_cap * 8, c->pool, s);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_sum, 64, c->pool, s);
+    auto release = [&]() {
+        if (d_kind) cudaFreeAsync(d_kind, s);
+        if (d_err) cudaFreeAsync(d_err, s);
+        if (d_val) cudaFreeAsync(d_val, s);
+        if (d_off) cudaFreeAsync(d_off, s);
+        if (d_sb) cudaFreeAsync(d_sb, s);
+        if (d_tape) cudaFreeAsync(d_tape, s);
+        if (d_sum) cudaFreeAsync(d_sum, s);
+    };
+    if (e != cudaSuccess) {
+        release();
+        cudaGetLastError();
+        return SJB200_MEMALLOC;
+    }
+    int32_t rc = sjb200_stage2_primitives_device_async(c, c->d_in, len, c->d_out, n, d_kind, d_err, d_val, d_off, d_sb, sb_cap, d_sum);
+    if (rc == SJB200_SUCCESS) rc = sjb200_stage2_tape_device_async(c, c->d_in, len, c->d_out, n, d_kind, d_err, d_val, d_off, d_tape, tp_cap, d_sum + 4);
+    uint64_t sum[8] = {};
+    if (rc == SJB200_SUCCESS) {
+        e = cudaMemcpyAsync(sum, d_sum, 64, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_err(e);
+    }
+    if (rc == SJB200_SUCCESS) {
+        const uint64_t sb = sum[1], tl = sum[6];
+        if (tape_len) *tape_len = tl;
+        if (strbuf_len) *strbuf_len = sb;
+        if (inexact_doubles) *inexact_doubles = sum[7];
+        rc = sum[4] == ~0ull ? SJB200_SUCCESS : (int32_t)(sum[4] & 0xFF);
+        if (rc == SJB200_SUCCESS && (tl > tape_capacity || sb > strbuf_capacity)) rc = SJB200_CAPACITY;
+        if (rc == SJB200_SUCCESS) {
+            e = cudaMemcpyAsync(tape_out, d_tape, tl * 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && sb) e = cudaMemcpyAsync(strbuf_out, d_sb, sb, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = cuda_err(e);
+        }
+    }
+    release();
+    return rc;
 }
 
 }  // extern "C"

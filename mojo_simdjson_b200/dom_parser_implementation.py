@@ -1,10 +1,11 @@
-"""Host-side mirror of the reference's parser facade for the stage-1 path.
+"""Host-side mirror of the reference's parser facade.
 
 Reference: src/mojo_simdjson/include/generic/dom_parser_implementation.mojo:15-89.  Same field names, same
-call (`stage1(buffer) -> ErrorType`), same error behaviour; the line that called
-JsonStructuralIndexer.index[128] (:69) calls libsimdjson_b200.so instead.  Stage 2 is not part of this path:
-a consumer reads `buf`, `length`, `structural_indexes[0 .. n+2]`, `n_structural_indexes` and
-`next_structural_index` exactly as the reference's JsonIterator does (json_iterator.mojo:28-38,256-288).
+calls (`stage1(buffer) -> ErrorType`, `stage2() -> ErrorType`), same error behaviour; the line that called
+JsonStructuralIndexer.index[128] (:69) calls libsimdjson_b200.so instead, and so does the one that called
+TapeBuilder.parse_document (:83).  A consumer that walks the index array itself reads `buf`, `length`,
+`structural_indexes[0 .. n+2]`, `n_structural_indexes` and `next_structural_index` exactly as the reference's
+JsonIterator does (json_iterator.mojo:28-38,256-288).
 """
 from __future__ import annotations
 
@@ -15,6 +16,53 @@ import numpy as np
 from . import _native, errors
 
 DEFAULT_MAX_LEN = 64 << 20
+
+JSON_VALUE_MASK = (1 << 56) - 1
+
+
+class Document:
+    """The reference's Document (include/dom/document.mojo:13-19): a tape and a string buffer."""
+
+    def __init__(self):
+        self.tape = np.zeros(0, dtype=np.uint64)
+        self.string_buf = np.zeros(0, dtype=np.uint8)
+        self.inexact_doubles = 0      # doubles outside the exact decimal -> binary fast path (not in the reference)
+
+    def string_at(self, offset: int) -> bytes:
+        n = int.from_bytes(self.string_buf[offset : offset + 4].tobytes(), "little")
+        return self.string_buf[offset + 4 : offset + 4 + n].tobytes()
+
+    def dump_raw_tape(self):
+        """The listing of include/dom/document.mojo:48-162, one line per tape word.  Returns (text, ok)."""
+        t = [int(x) for x in self.tape]
+        if not t or t[0] >> 56 != ord("r"):
+            return "", False
+        how_many = t[0] & JSON_VALUE_MASK
+        out = [f"0 : r\t// pointing to {how_many} (right after last node)"]
+        i = 1
+        while i < how_many - 1:
+            ty, payload = chr(t[i] >> 56), t[i] & JSON_VALUE_MASK
+            if ty == '"':
+                out.append(f'{i} : string "{self.string_at(payload).decode("utf-8", "replace")}"')
+            elif ty == "l":
+                v = t[i + 1]
+                out.append(f"{i} : integer {v - (1 << 64) if v >> 63 else v}")
+                i += 1
+            elif ty == "d":
+                out.append(f"{i} : float {float(np.array([t[i + 1]], dtype=np.uint64).view(np.float64)[0])}")
+                i += 1
+            elif ty in "tfn":
+                out.append(f"{i} : {dict(t='true', f='false', n='null')[ty]}")
+            elif ty in "{[":
+                out.append(f"{i} : {ty}\t// pointing to next tape location {payload & 0xFFFFFFFF} (first node after the scope),  saturated count "
+                           f"{(payload >> 32) & 0xFFFFFF}")
+            elif ty in "}]":
+                out.append(f"{i} : {ty}\t// pointing to previous tape location {payload & 0xFFFFFFFF} (start of the scope)")
+            else:
+                return "\n".join(out), False
+            i += 1
+        out.append(f"{how_many - 1} : r\t// pointing to {t[how_many - 1] & JSON_VALUE_MASK} (start root)")
+        return "\n".join(out) + "\n", True
 
 
 class DomParserImplementation:
@@ -29,6 +77,7 @@ class DomParserImplementation:
         self.n_structural_indexes = 0
         self.structural_indexes = np.zeros(0, dtype=np.uint32)
         self.next_structural_index = 0
+        self.document = Document()
         self.utf8_error = 0                          # not in the reference: its Utf8Checker is a stub
         self._capacity = 0
         self._max_depth = 100
@@ -88,4 +137,20 @@ class DomParserImplementation:
             # the reference assigns these only past its early returns (json_structural_indexer.mojo:160-174)
             self.n_structural_indexes = int(n.value)
             self.next_structural_index = 0
+        return rc
+
+    def stage2(self) -> int:
+        """reference :71-83 -- sizes the document's tape and string buffer, walks the structurals.  The walk runs on the
+        device over the copy of the document that stage1() left there; returns the error code."""
+        n, length = int(self.n_structural_indexes), int(self.length)
+        if self.buf is None or n == 0:
+            return errors.UNINITIALIZED
+        tape = np.zeros(2 * n + 2, dtype=np.uint64)
+        sbuf = np.zeros(length + 2 * n + 64, dtype=np.uint8)
+        tl, sl, inexact = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        rc = self._lib.sjb200_stage2(self._ctx, tape.ctypes.data, tape.size, sbuf.ctypes.data, sbuf.size, C.byref(tl), C.byref(sl), C.byref(inexact))
+        if rc == errors.SUCCESS:
+            self.document.tape = tape[: tl.value]
+            self.document.string_buf = sbuf[: sl.value]
+            self.document.inexact_doubles = int(inexact.value)
         return rc

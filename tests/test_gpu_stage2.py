@@ -234,3 +234,34 @@ def test_walk_fuzz(dev):
             continue
         run_walk(dev, data)
         done += 1
+
+
+def test_facade_stage1_then_stage2_like_the_reference_test():
+    """tests/test_stage_2.mojo:27-44, on the same four fixtures: stage1 -> 0, stage2 -> 0, dump_raw_tape succeeds; here also:
+    the tape decodes to what python's json parses (the reference test imports json.loads and stops there)."""
+    from mojo_simdjson_b200 import synth
+    from mojo_simdjson_b200.dom_parser_implementation import DomParserImplementation
+
+    parser = DomParserImplementation(0, max_len=8 << 20)
+    try:
+        docs = dict(cpu._fixture_inputs())
+        docs["twitter"] = bytes(synth.twitter_like())
+        docs["statuses"] = bytes(synth.status_array(1 << 20))
+        for name, data in docs.items():
+            assert parser.stage1(data) == 0, name
+            assert parser.stage2() == 0, name
+            text, ok = parser.document.dump_raw_tape()
+            assert ok and text.startswith("0 : r"), name
+            if parser.document.inexact_doubles == 0:
+                assert oracle.decode_tape(parser.document.tape, parser.document.string_buf) == cpu.python_document(data), name
+            w = oracle.stage1(data, impl="fast")
+            want = oracle.stage2_walk(data, w.indexes, w.n)
+            assert np.array_equal(parser.document.tape, want.tape) and np.array_equal(parser.document.string_buf, want.string_buf), name
+        # verdicts through the facade
+        for data, want in ((b"[1,]", 3), (b'{"a":tru}', 6), (b"[" * 120 + b"]" * 120, 4), (b'["\\q"]', 5), (b"[12x]", 9), (b"{}", 3)):
+            assert parser.stage1(data) == 0
+            assert parser.stage2() == want, data
+        assert parser.stage1(b'"abc') == 15          # stage 1 fails: stage 2 has nothing to walk
+        assert parser.stage2() == 12
+    finally:
+        parser.close()
