@@ -192,7 +192,7 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     if (e != cudaSuccess) return e;
     constexpr int FW = SJ_K3_FW;
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
-    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
+    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
 }
 // The stream pipeline (stage1_stream.cuh): classify -> span_scan -> flatten, stream ordered; the dependent
 // launches overlap their launch latency with their predecessor (programmatic dependent launch).
@@ -209,7 +209,7 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess)
-        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW - 1) / FW, FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
+        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
     c->launches += 3;
     return e;
 }

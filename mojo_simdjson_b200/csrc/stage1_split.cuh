@@ -246,22 +246,39 @@ __device__ __forceinline__ void flatten_chunk(const Stage1Params &P, uint32_t c,
     }
 }
 
-// chunks [chunk_begin, chunk_end): one warp each
+#ifndef SJ_K3_CPW
+#define SJ_K3_CPW 2   // consecutive chunks per warp of the flatten kernel: carries and mask words of all of them are requested up front
+#endif
+
+// chunks [chunk_begin, chunk_end): SJ_K3_CPW consecutive chunks per warp
 template <int FW>
 __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
     using Cfg = FlattenCfg<FW>;
+    constexpr uint32_t CPW = SJ_K3_CPW;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw) + warp * (Cfg::WCAP + 4);
-    const uint32_t c = chunk_begin + blockIdx.x * FW + warp;
+    const uint32_t c0 = chunk_begin + (blockIdx.x * FW + warp) * CPW;
     grid_dependency_wait();
-    if (c >= chunk_end) return;
-    const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carry
-    const uint64_t carry = __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c));
+    if (c0 >= chunk_end) return;
+    const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carries
+    uint64_t carry[CPW], structural[CPW];
+#pragma unroll
+    for (uint32_t j = 0; j < CPW; j++)
+        carry[j] = c0 + j < chunk_end ? __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c0 + j)) : 0ull;
     if (P.spec_flag && gave_up == P.gen) return;
-    const uint32_t s_w = (uint32_t)(carry >> 63);
-    const uint64_t structural = __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)c * 64 + s_w * 32 + lane));
-    flatten_chunk<Cfg::WCAP>(P, c, carry, structural, stage, lane);
+#pragma unroll
+    for (uint32_t j = 0; j < CPW; j++) {
+        const uint32_t s_w = (uint32_t)(carry[j] >> 63);
+        structural[j] = c0 + j < chunk_end ? __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)(c0 + j) * 64 + s_w * 32 + lane)) : 0ull;
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < CPW; j++) {
+        if (c0 + j < chunk_end) {
+            flatten_chunk<Cfg::WCAP>(P, c0 + j, carry[j], structural[j], stage, lane);
+            if (j + 1 < CPW) __syncwarp();   // the staging area is reused by the next chunk
+        }
+    }
 }
 
 #endif  // __CUDACC__
