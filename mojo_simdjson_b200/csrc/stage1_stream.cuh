@@ -63,9 +63,11 @@ struct StreamCfg {
 
 // phase 1 input of one lane from the warp's private buffer; `chunk` points at the chunk's first byte, HALO bytes before it
 // are the preceding input (chunk > 0).  `edge`: first chunk, or a last chunk that is not full.
+// `follows`: this warp has just processed chunk c - 1, whose carries out (`prev_tail`: bit 0 escaped, bit 1 scalar) are exact:
+// no look-behind needed (three of the four chunks of a run).
 template <bool UTF8>
 __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, bool edge, bool is_last,
-                                           uint32_t last_bytes, const Stage1Params &P, uint32_t &unresolved) {
+                                           uint32_t last_bytes, const Stage1Params &P, bool follows, uint32_t prev_tail, uint32_t &unresolved) {
     in.g0 = (int64_t)c * 2048 + lane * 64;
     const uint4 *src = reinterpret_cast<const uint4 *>(chunk + lane * 64);
 #pragma unroll
@@ -86,7 +88,10 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
         if (UTF8) in.prev = (in.g0 == 0) ? 0x20202020u : mask_word(in.prev, in.g0 - 4, (int64_t)P.mis, alen);
     }
     PrevState st = {0, 0, 0};
-    if (c > 0) {  // 32 bytes of look-behind, all inside the document (c >= 1, mis < 16)
+    if (follows) {
+        st.e = prev_tail & 1u;
+        st.p = (prev_tail >> 1) & 1u;
+    } else if (c > 0) {  // 32 bytes of look-behind, all inside the document (c >= 1, mis < 16)
         const uint32_t b = (uint32_t)chunk[-1 - lane];
         const uint32_t bsm = __ballot_sync(0xFFFFFFFFu, b == 0x5Cu);
         const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, b, 0);
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     uint32_t phase = 0;
     uint32_t parked = 0;           // lanes parked in `park` during the current run
     bool u8_bad = false;
+    uint32_t prev_c = NO_CHUNK - 1u, prev_tail = 0;   // the chunk this warp processed last and its carries out
     while (true) {
         mbar_wait(bar0 + 8 * b, phase);
         const uint32_t c = my_chunk[b];
@@ -277,13 +283,15 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             LaneInput in;
             uint32_t unresolved;
             const bool edge = (c == 0u) || (c == last && last_partial);
-            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, unresolved);
+            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, c == prev_c + 1u, prev_tail, unresolved);
             __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
             if (lane == 0) fetch(b);
             if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
                 *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
             warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
             parked += (uint32_t)__popc(ph.u8_lanes);
+            prev_c = c;
+            prev_tail = ph.tail;
         }
         uint64_t *mp = P.masks + (size_t)c * 64 + lane;
         st_mask(mp, ph.m0);
