@@ -49,6 +49,14 @@ __device__ __forceinline__ void st_mask(uint64_t *p, uint64_t v) {
 #endif
 }
 
+// One thread draws from the chunk counter.  Plain PTX: atomicAdd() makes the compiler aggregate over the active lanes (vote,
+// elect, shuffle), and that shuffle waits for the atomic at once -- here its result is not needed before the next run.
+__device__ __forceinline__ uint32_t ticket_draw(uint32_t *counter, uint32_t n) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(n) : "memory");
+    return old;
+}
+
 template <int NW>
 struct StreamCfg {
     static constexpr int THREADS = NW * 32;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
         if (t_left == 0) {
             t_cur = t_next;
             t_left = TICKET_CHUNKS;
-            t_next = t_base + atomicAdd(ticket, TICKET_CHUNKS);
+            t_next = t_base + ticket_draw(ticket, TICKET_CHUNKS);
         }
         const uint32_t c = t_cur + (TICKET_CHUNKS - t_left);
         t_left--;
