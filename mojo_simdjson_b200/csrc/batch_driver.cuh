@@ -160,8 +160,8 @@ int32_t batch_enqueue_gpu(sjb200_batch *b, int gi, uint32_t *d_idx, uint64_t idx
     const uint32_t nseg = (uint32_t)(g.seg_offsets.size() - 1);
     // this buffer set was last read by the exchange of two passes ago
     CK(cudaStreamWaitEvent(c->stream, g.xchg_done[set], 0));
-    // rows of segments that do not exist this pass must read {-1, -1}, whatever an earlier plan left there
-    CK(cudaMemsetAsync(g.d_rows[set], 0xFF, (size_t)b->max_segments * 8, c->stream));
+    // (rows of segments that do not exist read {-1, -1}: batch_reset_rows, whenever the plan changes -- not once per pass,
+    // a memset between two passes costs the GPU ~2 us)
     const int32_t rc = sjb200_batch_run_device_async(c, g.d_shard, g.seg_offsets.data(), 0, nseg, d_idx, g.idx_offsets.data(), idx_capacity,
                                                      g.d_rows[set], flags);
     CK(cudaEventRecord(g.pass_done[set], c->stream));
@@ -194,6 +194,17 @@ int32_t batch_exchange(sjb200_batch *b, int set) {
     for (BatchGpu &g : b->gpus) {
         CK(cudaSetDevice(g.ctx->device));
         CK(cudaEventRecord(g.xchg_done[set], g.xstream));
+    }
+    return SJB200_SUCCESS;
+}
+
+// a new plan: both row-buffer sets of a GPU read "no such segment" everywhere; the kernels then fill the rows that exist.
+// Stream ordered behind every exchange that still reads them.
+int32_t batch_reset_rows(sjb200_batch *b, BatchGpu &g) {
+    CK(cudaSetDevice(g.ctx->device));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaStreamWaitEvent(g.ctx->stream, g.xchg_done[k], 0));
+        CK(cudaMemsetAsync(g.d_rows[k], 0xFF, (size_t)b->max_segments * 8, g.ctx->stream));
     }
     return SJB200_SUCCESS;
 }
@@ -305,6 +316,8 @@ int32_t sjb200_batch_plan_resident(sjb200_batch *b, int32_t local_gpu, const uin
     uint32_t nseg = 0;
     const int32_t rc = sjb200_batch_split_device(g.ctx, d_shard, shard_len, b->seg_bytes, offs.data(), b->max_segments, &nseg);
     if (rc != SJB200_SUCCESS) return rc;
+    const int32_t rr = batch_reset_rows(b, g);
+    if (rr != SJB200_SUCCESS) return rr;
     g.d_shard = d_shard;
     g.seg_offsets.assign(offs.begin(), offs.begin() + nseg + 1);
     g.idx_offsets.assign(nseg + 1, 0);
@@ -401,12 +414,14 @@ int32_t sjb200_batch_run(sjb200_batch *b, const uint8_t *buf, uint64_t len, uint
         const uint64_t lo = shard[g], hi = shard[g + 1];
         if (hi > lo) CK(cudaMemcpyAsync(c->d_in, buf + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
         gp.d_shard = c->d_in;
+        {
+            const int32_t rr = batch_reset_rows(b, gp);   // the host entry point plans anew on every call
+            if (rr != SJB200_SUCCESS) return rr;
+        }
         if (gp.seg_offsets.size() >= 2) {
             const int32_t rc = batch_enqueue_gpu(b, g, c->d_out, c->d_out_cap, set, flags);
             if (rc != SJB200_SUCCESS) return rc;
         } else {
-            CK(cudaStreamWaitEvent(c->stream, gp.xchg_done[set], 0));
-            CK(cudaMemsetAsync(gp.d_rows[set], 0xFF, (size_t)b->max_segments * 8, c->stream));
             CK(cudaEventRecord(gp.pass_done[set], c->stream));
         }
     }

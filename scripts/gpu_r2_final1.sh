@@ -2,6 +2,8 @@
 # round 2, final single-GPU measurements of the committed build: all bench configurations, reference arm, size sweep, ncu launch list + full capture
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu_final.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final.log
+python __graft_entry__.py smoke > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_final.log
 timeout 600 python bench.py > gpurun_out/bench_final_doc1g.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_final_doc1g.log | cut -c1-250
 for cfg in small cjk dense runs; do
   timeout 600 python bench.py --config $cfg --steps 100 --warmup 10 > gpurun_out/bench_final_$cfg.log 2>&1; echo "bench $cfg rc=$?"; tail -1 gpurun_out/bench_final_$cfg.log | cut -c1-200
