@@ -516,7 +516,7 @@ int32_t sjb200_stage2_tape_device_async(sjb200_ctx *c, const uint8_t *d_buf, uin
                                         uint64_t *d_summary) {
     if (!c) return SJB200_UNINITIALIZED;
     if (!d_buf || !d_idx || !d_kind || !d_err || !d_value || !d_str_off || !d_tape || !d_summary) return SJB200_UNINITIALIZED;
-    if (len > 0xFFFFFFFFull || n > 0xFFFFFFF0ull) return SJB200_CAPACITY;
+    if (len > 0xFFFFFFFFull || n > 0x7FFFFFF0ull) return SJB200_CAPACITY;   // tape positions are 32 bit: 2 n + 2 words must fit
     if (n == 0) return SJB200_EMPTY;   // json_iterator.mojo:45-46 (at_eof)
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
