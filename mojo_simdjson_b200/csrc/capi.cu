@@ -217,8 +217,9 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
 int pick_warps(const sjb200_ctx *c, uint64_t alen) {
     if (c->forced_warps) return c->forced_warps;
     if (knobs().warps) return knobs().warps;
-    // small documents: smaller tiles so that the work spreads over all 148 SMs
-    if (alen >= (uint64_t)64 << 20) return 16;
+    // small documents: smaller tiles so that the work spreads over all 148 SMs (measured, tools/quickbench.py: 16-warp tiles
+    // win from 8 MiB on -- 8 MiB: 480 vs 411 GB/s, 16 MiB: 761 vs 718, 48 MiB: 1060 vs 996)
+    if (alen >= (uint64_t)8 << 20) return 16;
     if (alen >= (uint64_t)148 * 4 * 16384) return 8;
     if (alen >= (uint64_t)148 * 4 * 8192) return 4;
     return 2;
@@ -310,7 +311,7 @@ int32_t plan_document(sjb200_ctx *c, DocPlan &d, const uint8_t *d_buf, uint64_t 
             if (!auto_kind) return SJB200_UNEXPECTED_ERROR;
             kind = SJB200_KERNEL_PERSISTENT;   // chosen automatically: the persistent kernel has every shape
         } else {
-            d.warps = p.alen >= ((uint64_t)64 << 20) ? 16 : 8;
+            d.warps = 16;
         }
     }
     if (!valid_warps(d.warps)) return SJB200_UNEXPECTED_ERROR;
