@@ -48,6 +48,7 @@ struct Knobs {
     int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
     int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream
     uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
+    int flatten = 2;        // SJB200_FLATTEN=1: the lane-per-word flatten kernel instead of the balanced one (A/B measurements)
 };
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24; }
 const Knobs &knobs() {
@@ -60,6 +61,7 @@ const Knobs &knobs() {
             if (strcmp(e, "split") == 0) v.kernel = SJB200_KERNEL_SPLIT;
             if (strcmp(e, "stream") == 0) v.kernel = SJB200_KERNEL_STREAM;
         }
+        if (const char *e = getenv("SJB200_FLATTEN")) v.flatten = atoi(e) == 1 ? 1 : 2;
         if (const char *e = getenv("SJB200_CHUNK_MIB"))
             if (atoi(e) > 0) v.chunk_bytes = (uint64_t)atoi(e) << 20;
         return v;
@@ -143,6 +145,7 @@ template <int NW>
 cudaError_t prepare_split(int *occ) {
     using Cfg = SplitCfg<NW>;
     cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_flatten2_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_classify_kernel<NW, true>, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
 #ifndef SJ_STREAM_NW
@@ -155,6 +158,7 @@ cudaError_t prepare_stream(int *occ) {
     // cannot share an SM, and scan + flatten of one window must run beside the classify CTAs of the next
     cudaFuncSetAttribute(stage1_span_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(stage1_flatten2_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
 template <int NW, bool UTF8>
@@ -182,6 +186,14 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned b
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// flatten chunks [c0, c1) (c0 even): the balanced kernel (units of two chunks per warp) or, SJB200_FLATTEN=1, the lane-per-word one
+cudaError_t launch_flatten(const Stage1Params &p, uint32_t c0, uint32_t c1, cudaStream_t s, bool pdl) {
+    constexpr int FW = SJ_K3_FW;
+    if (knobs().flatten == 1)
+        return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, c0, c1);
+    return launch_dependent(stage1_flatten2_kernel<FW>, (c1 - c0 + FW * 2 - 1) / (FW * 2), Flatten2Cfg<FW>::THREADS, Flatten2Cfg<FW>::SMEM_BYTES, s, pdl, p, c0, c1);
+}
+
 template <int NW, bool UTF8>
 cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = SplitCfg<NW>;
@@ -190,16 +202,14 @@ cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     stage1_classify_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    constexpr int FW = SJ_K3_FW;
     const uint32_t c0 = p.tile_begin * NW, c1 = p.tile_end * NW;
-    return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, knobs().pdl != 0, p, c0, c1);
+    return launch_flatten(p, c0, c1, s, knobs().pdl != 0);
 }
 // The stream pipeline (stage1_stream.cuh): classify -> span_scan -> flatten, stream ordered; the dependent
 // launches overlap their launch latency with their predecessor (programmatic dependent launch).
 template <bool UTF8>
 cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = StreamCfg<STREAM_NW>;
-    constexpr int FW = SJ_K3_FW;
     const bool pdl = knobs().pdl != 0;
     const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
@@ -208,8 +218,7 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     cudaError_t e = cudaGetLastError();
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
-    if (e == cudaSuccess)
-        e = launch_dependent(stage1_flatten_kernel<FW>, (nchunks + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, 0u, nchunks);
+    if (e == cudaSuccess) e = launch_flatten(p, 0u, nchunks, s, pdl);
     c->launches += 3;
     return e;
 }

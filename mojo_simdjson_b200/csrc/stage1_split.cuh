@@ -281,6 +281,198 @@ __global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatte
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Balanced flatten.  stage1_flatten_kernel gives every lane the 64 bits of its own mask word: the extraction loop then
+// runs max-over-lanes trips (27.5 per chunk on the bench document for 10.3 indexes per lane on average -- 39 % of the
+// lanes do useful work).  Here a warp takes a UNIT of two consecutive chunks (4 KiB of input, ~660 indexes; lane t holds the
+// four 32-bit mask words of bytes [128 t, 128 t + 128)), and every lane extracts the SAME number q = ceil(K / 32) of
+// consecutive indexes of the unit's output:
+//   1. the unit's non-empty mask words are compacted into shared memory in stream order as 16-byte entries {word bit-reversed,
+//      index value of its bit 31, exclusive prefix count} (index = value - bfind(word)); the k-th empty word fills the k-th
+//      slot behind them with a sentinel, so all 128 slots are written;
+//   2. lane t binary-searches the prefix counts for the word that holds output t * q, drops the bits before it (a binary
+//      select, no loop), and then runs exactly q trips of {next word if this one is used up; find, clear, subtract, store}
+//      -- uniform trip count, no divergence, and with q forced odd the staging stores of the 32 lanes (stride q) never
+//      share a bank;
+//   3. the staged indexes go out as 16-byte vectors exactly as before.
+// Units with more than CAP indexes (denser than 0.19 structurals per byte) take the per-chunk path (flatten_chunk).
+// BitIndexer.write, reference json_structural_indexer.mojo:46-58.
+// ---------------------------------------------------------------------------------------------
+#ifndef SJ_FL2_CAP
+#define SJ_FL2_CAP 768
+#endif
+#ifndef SJ_FL2_MINCTAS
+#define SJ_FL2_MINCTAS 11
+#endif
+template <int FW>
+struct Flatten2Cfg {
+    static constexpr int THREADS = FW * 32;
+    static constexpr int CAP = SJ_FL2_CAP;                         // indexes of a unit flattened through the balanced path
+    static constexpr int QMAX = ((CAP + 31) / 32) | 1;            // trips per lane (odd)
+    static constexpr int STAGE = 32 * QMAX + 4;                   // every lane writes q slots (the last ones past K) + output phase
+    static constexpr int NVEC = (CAP + 3 + 3) / 4;                // 16-byte vectors the copy-out may have to move
+    static constexpr int ENT_OFF = STAGE * 4;                     // 128 entries {word bit-reversed, address of the next non-empty entry} + 1 sentinel
+    static constexpr int PX_OFF = ENT_OFF + 129 * 8 + 8;          // 128 exclusive prefix counts (16 bits)
+    static constexpr int WARP_BYTES = PX_OFF + 128 * 2;
+    static constexpr int SMEM_BYTES = FW * WARP_BYTES;
+    static_assert(STAGE >= 512 + 4, "the per-chunk fallback stages up to 512 indexes");
+    static_assert(WARP_BYTES % 16 == 0 && ENT_OFF % 16 == 0 && PX_OFF % 16 == 0, "16-byte vectors");
+};
+
+// q trips of the balanced extraction loop (q >= 1, warp-uniform).  w: current word (bit-reversed; may be 0 = used up), vb: the
+// index value of its bit 31, na: shared-memory address of the next non-empty entry {word, address of the one after it} (the
+// sentinel entry points at itself), sp: shared-memory address of this lane's first slot.  The value base of an entry follows
+// from its address: vb = 4 * address + vc (entries are 8 bytes and cover 32 input bytes each).
+__device__ __forceinline__ void flatten_balanced_loop(uint32_t w, uint32_t vb, uint32_t na, uint32_t sp, uint32_t q, uint32_t vc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, c;\n"
+        ".reg .u32 h, m, x, n;\n"
+        "mov.u32 n, %4;\n"
+        "FB_LOOP:\n"
+        "setp.eq.u32 p, %0, 0;\n"
+        "@p mad.lo.u32 %1, %2, 4, %5;\n"
+        "@p ld.shared.v2.u32 {%0, %2}, [%2];\n"
+        "bfind.u32 h, %0;\n"
+        "shl.b32 m, 1, h;\n"
+        "xor.b32 %0, %0, m;\n"
+        "sub.u32 x, %1, h;\n"
+        "st.shared.u32 [%3], x;\n"
+        "add.u32 %3, %3, 4;\n"
+        "sub.u32 n, n, 1;\n"
+        "setp.ne.u32 c, n, 0;\n"
+        "@c bra FB_LOOP;\n"
+        "}\n"
+        : "+r"(w), "+r"(vb), "+r"(na), "+r"(sp)
+        : "r"(q), "r"(vc)
+        : "memory");
+}
+
+// w (bit-reversed mask word) without its r highest set bits, r < popc(w): a binary descent to the largest `pos` whose top
+// `pos` bits hold exactly r set bits
+__device__ __forceinline__ uint32_t drop_high_bits(uint32_t w, uint32_t r) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const uint32_t c = (uint32_t)__popc((w << pos) >> (32 - s));   // set bits among the next s bits from the top
+        if (c <= r) {
+            r -= c;
+            pos += s;
+        }
+    }
+    return w & (0xFFFFFFFFu >> pos);
+}
+
+// stage[a .. a+total) -> out[first .. first+total) by one warp, total <= 4 * NV - 6: NV predicated 16-byte copies per lane
+// plus the ragged head / tail entries (a = phase of `first` in its 16-byte line, so stage and out are congruent)
+template <int NV>
+__device__ __forceinline__ void copy_out_warp_n(const uint32_t *stage, uint32_t a, uint32_t total, uint32_t *out, uint64_t first,
+                                                uint64_t cap, uint32_t lane) {
+    const uint32_t end = a + total;
+    uint32_t *g0 = out + ((int64_t)first - (int64_t)a);   // 16-byte aligned, may point below `out` by up to 3 entries
+    if (first + total <= cap) {
+        const uint32_t v_lo = (a + 3u) >> 2, v_hi = end >> 2;
+        const uint32_t nvec = v_hi > v_lo ? v_hi - v_lo : 0u;      // whole vectors; none when the run is shorter than a line
+        const uint4 *sv = reinterpret_cast<const uint4 *>(stage) + lane;
+        uint4 *gv = reinterpret_cast<uint4 *>(g0) + lane;
+#pragma unroll
+        for (int k = 0; k < (NV + 31) / 32; k++) {
+            const uint32_t v = lane + 32u * k;
+            if (v - v_lo < nvec) gv[32 * k] = sv[32 * k];          // v_lo <= v < v_hi in one unsigned compare
+        }
+        if (lane < 8u) {
+            const uint32_t j = lane < 4u ? lane : 4u * v_hi + (lane - 4u);
+            const bool head = lane < 4u && j >= a && j < end && j < 4u * v_lo;
+            const bool tail = lane >= 4u && j < end && j >= a && v_hi >= v_lo;
+            if (head || tail) g0[j] = stage[j];
+        }
+    } else {
+        for (uint32_t j = a + lane; j < end; j += 32u)
+            if (first + (j - a) < cap) g0[j] = stage[j];
+    }
+}
+
+// units of two chunks in [chunk_begin, chunk_end): unit u = chunks chunk_begin + 2u and + 1 (the last one may be missing)
+template <int FW>
+__global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
+    using Cfg = Flatten2Cfg<FW>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase);
+    const uint32_t ent0 = smem_u32(wbase + Cfg::ENT_OFF), px0 = smem_u32(wbase + Cfg::PX_OFF);
+    const uint32_t c0 = chunk_begin + (blockIdx.x * FW + warp) * 2u;
+    grid_dependency_wait();
+    if (c0 >= chunk_end) return;
+    const bool two = c0 + 1u < chunk_end;
+    const uint32_t half = lane >> 4;                       // lanes 16..31 hold chunk c0 + 1
+    const bool have = half == 0u || two;
+    const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carries
+    const uint64_t carry = have ? __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c0 + half)) : 0ull;
+    if (P.spec_flag && gave_up == P.gen) return;
+    // this lane's 128 input bytes = two consecutive 64-bit words of its chunk's plane
+    uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+    if (have) {
+        const uint8_t *mp = reinterpret_cast<const uint8_t *>(P.masks) + (size_t)(c0 + half) * 512u + ((uint32_t)(carry >> 63) * 256u + (lane & 15u) * 16u);
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mw.x), "=r"(mw.y), "=r"(mw.z), "=r"(mw.w) : "l"(mp) : "memory");
+    }
+    const uint32_t na = (uint32_t)__popc(mw.x), nb = na + (uint32_t)__popc(mw.y), nc = nb + (uint32_t)__popc(mw.z), n = nc + (uint32_t)__popc(mw.w);
+    const uint32_t incl = warp_inclusive_sum(n);
+    const uint32_t Kt = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint64_t first = __shfl_sync(0xFFFFFFFFu, (unsigned long long)carry, 0) & CARRY_RANK_MASK;   // the unit's indexes are out[first .. first + Kt)
+    if (Kt > (uint32_t)Cfg::CAP) {   // a dense unit: chunk by chunk, one 64-bit word per lane
+        for (uint32_t j = 0; j < (two ? 2u : 1u); j++) {
+            const uint64_t cj = __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c0 + j));
+            const uint64_t sj = __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)(c0 + j) * 64 + (uint32_t)(cj >> 63) * 32 + lane));
+            flatten_chunk<512>(P, c0 + j, cj, sj, stage, (int)lane);
+            __syncwarp();
+        }
+        return;
+    }
+    if (Kt == 0u) return;
+    const uint32_t sentinel = ent0 + 128u * 8u;
+    {   // entries of this lane's four words (32 contiguous bytes) and their prefix counts (8 contiguous bytes)
+        const uint32_t e = incl - n;
+        const uint32_t mine = ent0 + lane * 32u;
+        // the next non-empty word after this lane's: the first one of the next lane that has any
+        const uint32_t any = __ballot_sync(0xFFFFFFFFu, n != 0u);
+        const uint32_t above = any & (0xFFFFFFFEu << lane);
+        const uint32_t f = mw.x ? 0u : mw.y ? 8u : mw.z ? 16u : 24u;          // byte offset of this lane's first non-empty entry
+        const uint32_t src = (uint32_t)__ffs((int)above) - 1u;                 // (31 if there is none: value unused)
+        const uint32_t fs = __shfl_sync(0xFFFFFFFFu, f, src & 31u);
+        const uint32_t a3 = above ? ent0 + src * 32u + fs : sentinel;
+        const uint32_t a2 = mw.w ? mine + 24u : a3;
+        const uint32_t a1 = mw.z ? mine + 16u : a2;
+        const uint32_t a0 = mw.y ? mine + 8u : a1;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(mine), "r"(__brev(mw.x)), "r"(a0), "r"(__brev(mw.y)), "r"(a1) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(mine + 16u), "r"(__brev(mw.z)), "r"(a2), "r"(__brev(mw.w)), "r"(a3) : "memory");
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(px0 + lane * 8u), "r"(e | ((e + na) << 16)), "r"((e + nb) | ((e + nc) << 16)) : "memory");
+        if (lane == 0u) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sentinel), "r"(0xFFFFFFFFu), "r"(sentinel) : "memory");
+    }
+    __syncwarp();
+    // this lane's share: outputs [j0, j0 + q)
+    const uint32_t q = ((Kt + 31u) >> 5) | 1u;
+    const uint32_t j0 = lane * q;
+    // the last word whose exclusive prefix count is <= j0 (word 0 has count 0); among equal counts the last word is the
+    // non-empty one (empty words repeat the count of the non-empty word that follows them)
+    const uint8_t *pp = wbase + Cfg::PX_OFF;
+#pragma unroll
+    for (uint32_t step = 64u; step; step >>= 1)
+        if ((uint32_t)*reinterpret_cast<const uint16_t *>(pp + step * 2u) <= j0) pp += step * 2u;
+    const uint32_t k8 = (uint32_t)(pp - (wbase + Cfg::PX_OFF)) * 4u;          // byte offset of that word's entry
+    const uint2 e = *reinterpret_cast<const uint2 *>(wbase + Cfg::ENT_OFF + k8);
+    const uint32_t r = j0 - (uint32_t)*reinterpret_cast<const uint16_t *>(pp);
+    // the bits of that word that belong to the lanes before this one are dropped; a lane past the end starts used up
+    const bool live = j0 < Kt;
+    const uint32_t w = live ? drop_high_bits(e.x, r) : 0u;
+    const uint32_t vc = c0 * 2048u - P.mis + 31u - 4u * ent0;                 // value base of the entry at address A: 4 A + vc
+    const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
+    flatten_balanced_loop(w, 4u * (ent0 + k8) + vc, live ? e.y : sentinel, smem_u32(stage + a + j0), q, vc);
+    __syncwarp();
+    copy_out_warp_n<Cfg::NVEC>(stage, a, Kt, P.out, first, P.cap, lane);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace sjb200
