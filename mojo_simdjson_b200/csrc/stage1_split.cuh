@@ -352,12 +352,13 @@ __device__ __forceinline__ void flatten_balanced_loop(uint32_t w, uint32_t vb, u
 // w (bit-reversed mask word) without its r highest set bits, r < popc(w): a binary descent to the largest `pos` whose top
 // `pos` bits hold exactly r set bits
 __device__ __forceinline__ uint32_t drop_high_bits(uint32_t w, uint32_t r) {
-    uint32_t pos = 0;
+    uint32_t ws = w, pos = 0;   // ws = w << pos
 #pragma unroll
     for (int s = 16; s; s >>= 1) {
-        const uint32_t c = (uint32_t)__popc((w << pos) >> (32 - s));   // set bits among the next s bits from the top
+        const uint32_t c = (uint32_t)__popc(ws >> (32 - s));   // set bits among the next s bits from the top
         if (c <= r) {
             r -= c;
+            ws <<= s;
             pos += s;
         }
     }

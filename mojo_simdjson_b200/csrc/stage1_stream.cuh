@@ -31,7 +31,10 @@
 #define SJ_STREAMREG 64
 #endif
 #ifndef SJ_STREAM_DEPTH
-#define SJ_STREAM_DEPTH 3
+#define SJ_STREAM_DEPTH 2
+#endif
+#ifndef SJ_TICKET_CHUNKS
+#define SJ_TICKET_CHUNKS 4
 #endif
 #ifndef SJ_MASK_STORE
 #define SJ_MASK_STORE 1   // 1: streaming stores (the planes of a large document do not fit the L2 anyway), 0: write-back stores
@@ -63,30 +66,45 @@ struct StreamCfg {
     static constexpr int DEPTH = SJ_STREAM_DEPTH;
     static constexpr int HALO = 32;
     static constexpr int BUF = 2048 + HALO;                 // 16-byte multiple
-    static constexpr int PARK = 32 * 80;                    // 32 parked UTF-8 lanes of 80 B per warp (a run of 4 chunks parks <= 8 each)
+    static constexpr int PARK = SJ_TICKET_CHUNKS * SJ_U8_DEFER_MAX * 80;   // parked UTF-8 lanes of 80 B per warp (a run of 4 chunks parks <= 8 each)
     static constexpr int WARP_BYTES = DEPTH * BUF + PARK;
     static constexpr int SMEM_BYTES = NW * WARP_BYTES;
     static constexpr int MAXREG = SJ_STREAMREG;
 };
 
-// phase 1 input of one lane from the warp's private buffer; `chunk` points at the chunk's first byte, HALO bytes before it
-// are the preceding input (chunk > 0).  `edge`: first chunk, or a last chunk that is not full.
+// phase 1 input of one lane from the warp's private buffer; `chunk` is the shared-space address of the chunk's first byte, HALO
+// bytes before it are the preceding input (chunk > 0).  `edge`: first chunk, or a last chunk that is not full.
 // `follows`: this warp has just processed chunk c - 1, whose carries out (`prev_tail`: bit 0 escaped, bit 1 scalar) are exact:
 // no look-behind needed (three of the four chunks of a run).
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 template <bool UTF8>
-__device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, int lane, uint32_t c, bool edge, bool is_last,
-                                           uint32_t last_bytes, const Stage1Params &P, bool follows, uint32_t prev_tail, uint32_t &unresolved) {
+__device__ __forceinline__ void chunk_load(LaneInput &in, uint32_t chunk /* shared-space address of the chunk's first byte */, int lane, uint32_t c, bool edge,
+                                           bool is_last, uint32_t last_bytes, const Stage1Params &P, bool follows, uint32_t prev_tail, uint32_t &unresolved) {
     in.g0 = (int64_t)c * 2048 + lane * 64;
-    const uint4 *src = reinterpret_cast<const uint4 *>(chunk + lane * 64);
+    const uint32_t src = chunk + (uint32_t)lane * 64u;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const uint4 v = src[q];
+        const uint4 v = lds_u4(src + 16u * q);
         in.w[4 * q + 0] = v.x;
         in.w[4 * q + 1] = v.y;
         in.w[4 * q + 2] = v.z;
         in.w[4 * q + 3] = v.w;
     }
-    in.prev = UTF8 ? *reinterpret_cast<const uint32_t *>(chunk + lane * 64 - 4) : 0u;
+    in.prev = UTF8 ? lds_u32(src - 4u) : 0u;
     // the document may end exactly with this lane's last byte (also when the last chunk is full: not an "edge" chunk then)
     in.ends = is_last && ((uint32_t)lane * 64u + 64u == last_bytes);
     if (edge) {  // bytes outside [mis, alen) read as 0x20 (reference tail padding)
@@ -100,7 +118,7 @@ __device__ __forceinline__ void chunk_load(LaneInput &in, const uint8_t *chunk, 
         st.e = prev_tail & 1u;
         st.p = (prev_tail >> 1) & 1u;
     } else if (c > 0) {  // 32 bytes of look-behind, all inside the document (c >= 1, mis < 16)
-        const uint32_t b = (uint32_t)chunk[-1 - lane];
+        const uint32_t b = lds_u8(chunk - 1u - (uint32_t)lane);
         const uint32_t bsm = __ballot_sync(0xFFFFFFFFu, b == 0x5Cu);
         const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, b, 0);
         st = prev_state(bsm, 32, c1);
@@ -190,9 +208,6 @@ __device__ __forceinline__ bool resolve_long_runs(const Stage1Params &P, uint32_
 // kernel that follows resets it).  A static partition would be slightly cheaper but assumes that every CTA of the grid is
 // resident from the start: with another kernel on the device (the NCCL verdict exchange of the previous pass, a second
 // context) a displaced CTA would start only when some other CTA has finished its whole share, doubling the kernel time.
-#ifndef SJ_TICKET_CHUNKS
-#define SJ_TICKET_CHUNKS 4
-#endif
 constexpr uint32_t TICKET_CHUNKS = SJ_TICKET_CHUNKS;
 constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
 
@@ -218,6 +233,11 @@ __device__ __forceinline__ bool validate_parked_lanes(const uint8_t *park, uint3
 }
 
 // chunks [chunk_begin, chunk_end) of the document (chunk_begin a multiple of TICKET_CHUNKS; the pipeline passes the whole document)
+//
+// Ring of DEPTH private buffers per warp.  The bookkeeping (which chunk sits in which buffer, the run being worked on, the
+// next run) is kept in registers by ALL lanes -- straight-line, warp-uniform code; only the bulk copy itself and the atomic
+// draw are issued by lane 0.  A chunk number >= chunk_end means "nothing more": tickets only grow, so once a buffer holds
+// such a number every later one does too, and no copy is outstanding when the warp leaves.
 template <int NW, bool UTF8>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks,
                                                                                                             uint32_t chunk_begin, uint32_t chunk_end) {
@@ -226,96 +246,101 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     static_assert(TICKET_CHUNKS * SJ_U8_DEFER_MAX <= 32, "a run must not park more lanes than the warp's slots hold");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
-    __shared__ uint32_t s_chunk[NW * DEPTH];                  // chunk held by each buffer, NO_CHUNK = nothing more to do
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
     const uint32_t buf0 = smem_u32(wbase);                    // shared-space addresses: 32-bit arithmetic only
-    const uint8_t *bufs = wbase;
     uint8_t *park = wbase + DEPTH * Cfg::BUF;                 // parked UTF-8 lanes of the current run
     const uint32_t bar0 = smem_u32(&s_bar[warp * DEPTH]);
-    volatile uint32_t *my_chunk = s_chunk + warp * DEPTH;
     uint32_t *ticket = P.ticket + 3, *exits = P.ticket + 5;
     // every chunk is 2048 bytes except possibly the last one; every chunk but chunk 0 has HALO bytes of look-behind
     const uint32_t last = nchunks - 1u;
     const uint32_t last_bytes = (uint32_t)(P.alen - (uint64_t)last * 2048u);   // 1 .. 2048
     const uint32_t last_tx = (last_bytes + 15u) & ~15u;                        // stays inside the last 16-byte line of the data
     const bool last_partial = last_bytes < 2048u;
+    const uint8_t *src0 = P.abase - Cfg::HALO;                                 // chunk c with its look-behind starts at src0 + 2048 c
 
-    // lane 0 only: the next chunk of this warp.  The draw for the ticket after the current one is already in flight, so the
-    // atomic's latency is never waited for.
     // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3 of the window), so that a launch does not begin with
-    // thousands of atomics on one address; the counter hands out the chunks after those.
+    // thousands of atomics on one address; the counter hands out the runs after those.  The draw for the run after the
+    // current one is always in flight (lane 0 holds its result), so the atomic's latency is never waited for.
     const uint32_t t_base = chunk_begin + gridDim.x * NW * TICKET_CHUNKS;
-    uint32_t t_cur = 0, t_left = 0, t_next = chunk_begin + (blockIdx.x * NW + warp) * TICKET_CHUNKS;
-    auto next_chunk = [&]() -> uint32_t {
-        if (t_left == 0) {
-            t_cur = t_next;
+    uint32_t t_cur = chunk_begin + (blockIdx.x * NW + warp) * TICKET_CHUNKS, t_left = TICKET_CHUNKS;
+    uint32_t drawn = lane == 0 ? ticket_draw(ticket, TICKET_CHUNKS) : 0u;      // lane 0: the run after this one (relative to t_base)
+    auto next_chunk = [&]() -> uint32_t {   // warp-uniform
+        if (t_left == 0u) {
+            t_cur = t_base + __shfl_sync(0xFFFFFFFFu, drawn, 0);
             t_left = TICKET_CHUNKS;
-            t_next = t_base + ticket_draw(ticket, TICKET_CHUNKS);
+            if (lane == 0) drawn = ticket_draw(ticket, TICKET_CHUNKS);
         }
-        const uint32_t c = t_cur + (TICKET_CHUNKS - t_left);
         t_left--;
-        return c;
+        return t_cur++;
     };
-    // lane 0 only: refill buffer b with the warp's next chunk (bulk copy of the chunk and its look-behind), or mark the end
-    auto fetch = [&](int b) {
-        const uint32_t c = next_chunk();
-        if (c < chunk_end) {
-            my_chunk[b] = c;
+    // lane 0: start the bulk copy of chunk c (< chunk_end) and its look-behind into buffer b
+    auto issue = [&](int b, uint32_t c) {
+        const uint32_t bar = bar0 + 8u * b, dst = buf0 + b * Cfg::BUF;
+        if (c - 1u < last - 1u) {   // 0 < c < last: the common case, constant size
+            mbar_expect_tx(bar, 2048u + Cfg::HALO);
+            bulk_load(dst, src0 + (size_t)c * 2048u, 2048u + Cfg::HALO, bar);
+        } else {
             const uint32_t halo = c > 0u ? (uint32_t)Cfg::HALO : 0u;
             const uint32_t tx = (c == last ? last_tx : 2048u) + halo;
-            mbar_expect_tx(bar0 + 8 * b, tx);
-            bulk_load(buf0 + b * Cfg::BUF + Cfg::HALO - halo, P.abase + (size_t)c * 2048u - halo, tx, bar0 + 8 * b);
-        } else {
-            my_chunk[b] = NO_CHUNK;
-            mbar_arrive(bar0 + 8 * b);
+            mbar_expect_tx(bar, tx);
+            bulk_load(dst + Cfg::HALO - halo, P.abase + (size_t)c * 2048u - halo, tx, bar);
         }
     };
+    uint32_t held[DEPTH];          // the chunk each buffer holds (all lanes)
     if (lane == 0) {
         for (int b = 0; b < DEPTH; b++) mbar_init(bar0 + 8 * b, 1);
         fence_mbar_init();
-        for (int b = 0; b < DEPTH; b++) fetch(b);
     }
     __syncwarp();
-    int b = 0;
+#pragma unroll
+    for (int b = 0; b < DEPTH; b++) {
+        held[b] = next_chunk();
+        if (lane == 0 && held[b] < chunk_end) issue(b, held[b]);
+    }
     uint32_t phase = 0;
     uint32_t parked = 0;           // lanes parked in `park` during the current run
     bool u8_bad = false;
     uint32_t prev_c = NO_CHUNK - 1u, prev_tail = 0;   // the chunk this warp processed last and its carries out
-    while (true) {
-        mbar_wait(bar0 + 8 * b, phase);
-        const uint32_t c = my_chunk[b];
-        if (c == NO_CHUNK) break;
-        LanePhase1 ph;
-        {
-            LaneInput in;
-            uint32_t unresolved;
-            const bool edge = (c == 0u) || (c == last && last_partial);
-            chunk_load<UTF8>(in, bufs + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, c == prev_c + 1u, prev_tail, unresolved);
-            __syncwarp();  // every lane has its bytes (and the chunk number) in registers: the buffer can be refilled
-            if (lane == 0) fetch(b);
-            if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
-                *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
-            warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
-            parked += (uint32_t)__popc(ph.u8_lanes);
-            prev_c = c;
-            prev_tail = ph.tail;
+    bool done = false;
+    while (!done) {
+#pragma unroll
+        for (int b = 0; b < DEPTH; b++) {   // static buffer index: no address arithmetic on it
+            const uint32_t c = held[b];
+            if (c >= chunk_end) {
+                done = true;
+                break;
+            }
+            mbar_wait(bar0 + 8 * b, phase);
+            LanePhase1 ph;
+            {
+                LaneInput in;
+                uint32_t unresolved;
+                const bool edge = (c == 0u) || (c == last && last_partial);
+                chunk_load<UTF8>(in, buf0 + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, c == prev_c + 1u, prev_tail, unresolved);
+                __syncwarp();  // every lane has its bytes in registers: the buffer can be refilled
+                held[b] = next_chunk();
+                if (lane == 0 && held[b] < chunk_end) issue(b, held[b]);
+                if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
+                    *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
+                warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
+                parked += (uint32_t)__popc(ph.u8_lanes);
+                prev_c = c;
+                prev_tail = ph.tail;
+            }
+            uint64_t *mp = P.masks + (size_t)c * 64 + lane;
+            st_mask(mp, ph.m0);
+            st_mask(mp + 32, ph.m1);
+            if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
+            if (UTF8 && parked && ((c & (TICKET_CHUNKS - 1u)) == TICKET_CHUNKS - 1u || c + 1u == chunk_end)) {
+                // end of a run: the lanes whose validation was deferred, 32 at a time
+                __syncwarp();
+                u8_bad |= validate_parked_lanes(park, parked, lane);
+                parked = 0;
+                __syncwarp();
+            }
         }
-        uint64_t *mp = P.masks + (size_t)c * 64 + lane;
-        st_mask(mp, ph.m0);
-        st_mask(mp + 32, ph.m1);
-        if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
-        if (++b == DEPTH) {
-            b = 0;
-            phase ^= 1u;
-        }
-        if (UTF8 && parked && ((c & (TICKET_CHUNKS - 1u)) == TICKET_CHUNKS - 1u || c + 1u == chunk_end)) {
-            // end of a run: the lanes whose validation was deferred, 32 at a time
-            __syncwarp();
-            u8_bad |= validate_parked_lanes(park, parked, lane);
-            parked = 0;
-            __syncwarp();
-        }
+        phase ^= 1u;
     }
     // a violation among the deferred lanes: the document's last launch folds it into the verdict (stage1_persistent.cuh)
     if (UTF8 && u8_bad && lane == 0) P.spec_flag[1] = P.gen;
