@@ -161,14 +161,6 @@ cudaError_t prepare_stream(int *occ) {
     cudaFuncSetAttribute(stage1_flatten2_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
-template <int NW, bool UTF8>
-cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
-    using Cfg = PersistCfg<NW>;
-    const unsigned span = p.tile_end - p.tile_begin;
-    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
-    stage1_persistent_kernel<NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
-}
 // Launch `kernel` so that it may be scheduled while the previous kernel of the stream drains (programmatic dependent
 // launch); the kernel itself waits for its predecessor (griddepcontrol.wait) before it reads anything.
 template <typename... KArgs, typename... Args>
@@ -185,7 +177,14 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned b
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-
+template <int NW, bool UTF8>
+cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) {
+    using Cfg = PersistCfg<NW>;
+    const unsigned span = p.tile_end - p.tile_begin;
+    const unsigned grid = span < (unsigned)max_ctas ? span : (unsigned)max_ctas;
+    // as the fallback of the stream pipeline (spec_flag set) it follows the flatten kernel as a dependent launch
+    return launch_dependent(stage1_persistent_kernel<NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, p.spec_flag != nullptr && knobs().pdl != 0, p);
+}
 // flatten chunks [c0, c1) (c0 even): the balanced kernel (units of two chunks per warp) or, SJB200_FLATTEN=1, the lane-per-word one
 cudaError_t launch_flatten(const Stage1Params &p, uint32_t c0, uint32_t c1, cudaStream_t s, bool pdl) {
     constexpr int FW = SJ_K3_FW;
@@ -214,8 +213,8 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const uint32_t nchunks = (uint32_t)((p.alen + 2047) / 2048);
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
-    stage1_stream_classify_kernel<STREAM_NW, UTF8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p, nchunks, 0u, nchunks);
-    cudaError_t e = cudaGetLastError();
+    // (the first launch of a document is a dependent launch too: back-to-back documents overlap their launch latencies)
+    cudaError_t e = launch_dependent(stage1_stream_classify_kernel<STREAM_NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, pdl, p, nchunks, 0u, nchunks);
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_flatten(p, 0u, nchunks, s, pdl);

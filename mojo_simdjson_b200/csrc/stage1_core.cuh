@@ -308,14 +308,26 @@ SJ_HD uint64_t escaped_mask(uint64_t bs, uint64_t e_in) {
     return code ^ (bs | e_in);
 }
 
+// prefix xor of a 64-bit word, done on its two halves (the left shifts of 32-bit words run on the FMA pipe as multiplications;
+// a 64-bit shift would cost a funnel shift on the ALU pipe per step); the parity of the low half then flips the high half
 SJ_HD uint64_t prefix_xor64(uint64_t x) {
-    x ^= x << 1;
-    x ^= x << 2;
-    x ^= x << 4;
-    x ^= x << 8;
-    x ^= x << 16;
-    x ^= x << 32;
-    return x;
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    lo ^= lo << 1;
+    hi ^= hi << 1;
+    lo ^= lo << 2;
+    hi ^= hi << 2;
+    lo ^= lo << 4;
+    hi ^= hi << 4;
+    lo ^= lo << 8;
+    hi ^= hi << 8;
+    lo ^= lo << 16;
+    hi ^= hi << 16;
+#if defined(__CUDA_ARCH__)
+    hi ^= (uint32_t)__mulhi((int)lo, 2);        // all ones iff bit 31 of lo is set (IMAD.HI)
+#else
+    hi ^= 0u - (lo >> 31);
+#endif
+    return ((uint64_t)hi << 32) | lo;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -108,6 +108,11 @@ __device__ __forceinline__ uint64_t gtime() {
 // A no-op when the kernel was launched without the attribute.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lanemask_lt() {   // bits of the lanes below this one
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -363,7 +368,7 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 // the k-th flagged lane parks its bit planes, the 4 bytes before it and its end-of-document bit in slot k
                 r.u8_lanes = hi_lanes;
                 if (any_hi) {
-                    uint4 *s = u8_slots + 5 * __popc(hi_lanes & ((1u << lane) - 1u));   // 80 contiguous bytes per slot
+                    uint4 *s = u8_slots + 5 * __popc(hi_lanes & lanemask_lt());   // 80 contiguous bytes per slot
                     s[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     s[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
                     s[2] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -388,15 +393,18 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
     // escapes and quotes, exact; structural bits for both in-string parities
     // A = lanes that are one long backslash run, O = parity of the backslash run each lane ends with; both are zero unless
     // some lane ends in a backslash, which one ballot on the top bit decides
-    uint32_t bA = 0, bO = 0;
+    // Without such a lane no escape crosses a lane boundary: lane 0 inherits the warp's carry, every other lane starts clean.
+    const uint32_t lt = lanemask_lt();
+    uint32_t e_in = lane ? 0u : in.wst.e, e_out = 0u;
     if (__ballot_sync(0xFFFFFFFFu, (uint32_t)(m.bs >> 32) >> 31)) {
-        bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
-        bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
+        const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));
+        const uint32_t bO = __ballot_sync(0xFFFFFFFFu, lane_trailing_run_parity(m.bs));
+        e_in = warp_lane_e_in(bA, bO, lane, in.wst.e);
+        e_out = warp_lane_e_in(bA, bO, 32, in.wst.e);
     }
-    const LaneQuotes q = lane_quotes(m, warp_lane_e_in(bA, bO, lane, in.wst.e));
+    const LaneQuotes q = lane_quotes(m, e_in);
     const uint32_t bPB = __ballot_sync(0xFFFFFFFFu, (q.ps >> 63) != 0);
     const uint32_t bNQ = __ballot_sync(0xFFFFFFFFu, (q.nqs >> 63) != 0);
-    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t rel = (uint32_t)__popc(bPB & lt) & 1u;
     const uint32_t p_in = lane ? ((bNQ >> (lane - 1)) & 1u) : in.wst.p;
     const LaneDual dual = lane_structurals_dual(m, q, rel, p_in);
@@ -408,7 +416,7 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
     r.wc0 = __reduce_add_sync(0xFFFFFFFFu, r.c0);
     r.wc1 = __reduce_add_sync(0xFFFFFFFFu, r.c1);
     r.wflags = __reduce_or_sync(0xFFFFFFFFu, (dual.u0 << 1) | (dual.u1 << 2) | (u8err << 3)) | ((uint32_t)__popc(bPB) & 1u);
-    r.tail = warp_lane_e_in(bA, bO, 32, in.wst.e) | ((bNQ >> 31) << 1);
+    r.tail = e_out | ((bNQ >> 31) << 1);
 }
 
 // combine the warp summaries of a tile (called by one full warp): the tile aggregate, and for every warp (lane < nwarps)

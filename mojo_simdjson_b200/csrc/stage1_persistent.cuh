@@ -60,7 +60,8 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(PersistCfg<NW>::MAX
     __shared__ uint32_t s_loaded;               // compute warps that have pulled the current tile into registers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (P.spec_flag && __ldg(P.spec_flag) != P.gen) {
+    grid_dependency_wait();   // as the pipeline's fallback it is launched while the flatten kernel drains (a no-op otherwise)
+    if (P.spec_flag && __ldcg(P.spec_flag) != P.gen) {
         // launched as the exact fallback of the stream pipeline (stage1_stream.cuh) and not needed: only keep the
         // ticket-counter alternation intact
         if (blockIdx.x == 0 && tid == 0) {

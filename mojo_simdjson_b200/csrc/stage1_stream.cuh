@@ -66,7 +66,7 @@ struct StreamCfg {
     static constexpr int DEPTH = SJ_STREAM_DEPTH;
     static constexpr int HALO = 32;
     static constexpr int BUF = 2048 + HALO;                 // 16-byte multiple
-    static constexpr int PARK = SJ_TICKET_CHUNKS * SJ_U8_DEFER_MAX * 80;   // parked UTF-8 lanes of 80 B per warp (a run of 4 chunks parks <= 8 each)
+    static constexpr int PARK = 32 * 80;                    // 32 parked UTF-8 lanes of 80 B per warp; validated when fewer than SJ_U8_DEFER_MAX slots are left
     static constexpr int WARP_BYTES = DEPTH * BUF + PARK;
     static constexpr int SMEM_BYTES = NW * WARP_BYTES;
     static constexpr int MAXREG = SJ_STREAMREG;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
                                                                                                             uint32_t chunk_begin, uint32_t chunk_end) {
     using Cfg = StreamCfg<NW>;
     constexpr int DEPTH = Cfg::DEPTH;
-    static_assert(TICKET_CHUNKS * SJ_U8_DEFER_MAX <= 32, "a run must not park more lanes than the warp's slots hold");
+    static_assert(SJ_U8_DEFER_MAX <= 32, "a chunk must not park more lanes than the warp's slots hold");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3 of the window), so that a launch does not begin with
     // thousands of atomics on one address; the counter hands out the runs after those.  The draw for the run after the
     // current one is always in flight (lane 0 holds its result), so the atomic's latency is never waited for.
+    grid_dependency_wait();   // launched while the previous kernel of the stream drains: nothing global is touched before this
     const uint32_t t_base = chunk_begin + gridDim.x * NW * TICKET_CHUNKS;
     uint32_t t_cur = chunk_begin + (blockIdx.x * NW + warp) * TICKET_CHUNKS, t_left = TICKET_CHUNKS;
     uint32_t drawn = lane == 0 ? ticket_draw(ticket, TICKET_CHUNKS) : 0u;      // lane 0: the run after this one (relative to t_base)
@@ -332,8 +333,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             st_mask(mp, ph.m0);
             st_mask(mp + 32, ph.m1);
             if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(ph.wc0, ph.wc1, ph.wflags, 0u);
-            if (UTF8 && parked && ((c & (TICKET_CHUNKS - 1u)) == TICKET_CHUNKS - 1u || c + 1u == chunk_end)) {
-                // end of a run: the lanes whose validation was deferred, 32 at a time
+            if (UTF8 && parked > 32u - SJ_U8_DEFER_MAX) {
+                // the next chunk might not find room: the lanes whose validation was deferred, up to 32 at a time
                 __syncwarp();
                 u8_bad |= validate_parked_lanes(park, parked, lane);
                 parked = 0;
@@ -341,6 +342,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
             }
         }
         phase ^= 1u;
+    }
+    if (UTF8 && parked) {   // the lanes still parked when the warp runs out of chunks
+        __syncwarp();
+        u8_bad |= validate_parked_lanes(park, parked, lane);
     }
     // a violation among the deferred lanes: the document's last launch folds it into the verdict (stage1_persistent.cuh)
     if (UTF8 && u8_bad && lane == 0) P.spec_flag[1] = P.gen;
