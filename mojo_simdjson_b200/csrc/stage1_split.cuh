@@ -312,13 +312,21 @@ struct Flatten2Cfg {
     static constexpr int QMAX = ((CAP + 31) / 32) | 1;            // trips per lane (odd)
     static constexpr int STAGE = 32 * QMAX + 4;                   // every lane writes q slots (the last ones past K) + output phase
     static constexpr int NVEC = (CAP + 3 + 3) / 4;                // 16-byte vectors the copy-out may have to move
-    static constexpr int ENT_OFF = STAGE * 4;                     // 128 entries {word bit-reversed, address of the next non-empty entry} + 1 sentinel
-    static constexpr int PX_OFF = ENT_OFF + 129 * 8 + 8;          // 128 exclusive prefix counts (16 bits)
-    static constexpr int WARP_BYTES = PX_OFF + 128 * 2;
+    // per warp: 128 entries {word bit-reversed, address of the next non-empty entry} in stream order (word j of lane t at
+    // 32 t + 8 j), the sentinel entry at 1024; the staging area; the prefix counts (four 16-bit values per lane); the lane
+    // that holds the first output of every lane's share
+    static constexpr int ENT_OFF = 0;
+    static constexpr int STAGE_OFF = 1024 + 16;
+    static constexpr int PX_OFF = STAGE_OFF + STAGE * 4;
+    static constexpr int TAB_OFF = PX_OFF + 256;
+    static constexpr int WARP_BYTES = ((TAB_OFF + 32) + 15) & ~15;
     static constexpr int SMEM_BYTES = FW * WARP_BYTES;
+    static_assert(QMAX < 64 && CAP + QMAX < 4200, "range of the division table");
     static_assert(STAGE >= 512 + 4, "the per-chunk fallback stages up to 512 indexes");
-    static_assert(WARP_BYTES % 16 == 0 && ENT_OFF % 16 == 0 && PX_OFF % 16 == 0, "16-byte vectors");
+    static_assert(STAGE_OFF % 16 == 0 && PX_OFF % 16 == 0, "16-byte vectors");
 };
+// floor(x / q) = (x * FL2_MAGIC[q]) >> 20 for x < 4200, q < 64 (checked exhaustively when the table was generated)
+__constant__ uint32_t FL2_MAGIC[64] = {0, 1048577, 524289, 349526, 262145, 209716, 174763, 149797, 131073, 116509, 104858, 95326, 87382, 80660, 74899, 69906, 65537, 61681, 58255, 55189, 52429, 49933, 47663, 45591, 43691, 41944, 40330, 38837, 37450, 36158, 34953, 33826, 32769, 31776, 30841, 29960, 29128, 28340, 27595, 26887, 26215, 25576, 24967, 24386, 23832, 23302, 22796, 22311, 21846, 21400, 20972, 20561, 20165, 19785, 19419, 19066, 18725, 18397, 18079, 17773, 17477, 17190, 16913, 16645};
 
 // q trips of the balanced extraction loop (q >= 1, warp-uniform).  w: current word (bit-reversed; may be 0 = used up), vb: the
 // index value of its bit 31, na: shared-memory address of the next non-empty entry {word, address of the one after it} (the
@@ -394,6 +402,10 @@ __device__ __forceinline__ void copy_out_warp_n(const uint32_t *stage, uint32_t 
     }
 }
 
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 // units of two chunks in [chunk_begin, chunk_end): unit u = chunks chunk_begin + 2u and + 1 (the last one may be missing)
 template <int FW>
 __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
@@ -401,8 +413,8 @@ __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kerne
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase);
-    const uint32_t ent0 = smem_u32(wbase + Cfg::ENT_OFF), px0 = smem_u32(wbase + Cfg::PX_OFF);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + Cfg::STAGE_OFF);
+    const uint32_t ent0 = smem_u32(wbase), px0 = smem_u32(wbase + Cfg::PX_OFF), tab0 = smem_u32(wbase + Cfg::TAB_OFF);
     const uint32_t c0 = chunk_begin + (blockIdx.x * FW + warp) * 2u;
     grid_dependency_wait();
     if (c0 >= chunk_end) return;
@@ -432,15 +444,16 @@ __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kerne
         return;
     }
     if (Kt == 0u) return;
-    const uint32_t sentinel = ent0 + 128u * 8u;
-    {   // entries of this lane's four words (32 contiguous bytes) and their prefix counts (8 contiguous bytes)
+    const uint32_t sentinel = ent0 + 1024u;
+    const uint32_t q = ((Kt + 31u) >> 5) | 1u;             // every lane's share: q consecutive outputs (odd: conflict-free staging stores)
+    {   // this lane's four entries, their prefix counts, and the lanes whose share starts inside its 128 bytes
         const uint32_t e = incl - n;
         const uint32_t mine = ent0 + lane * 32u;
         // the next non-empty word after this lane's: the first one of the next lane that has any
         const uint32_t any = __ballot_sync(0xFFFFFFFFu, n != 0u);
         const uint32_t above = any & (0xFFFFFFFEu << lane);
-        const uint32_t f = mw.x ? 0u : mw.y ? 8u : mw.z ? 16u : 24u;          // byte offset of this lane's first non-empty entry
-        const uint32_t src = (uint32_t)__ffs((int)above) - 1u;                 // (31 if there is none: value unused)
+        const uint32_t f = mw.x ? 0u : mw.y ? 8u : mw.z ? 16u : 24u;          // offset of this lane's first non-empty entry
+        const uint32_t src = (uint32_t)__ffs((int)above) - 1u;                 // (none: the value is not used)
         const uint32_t fs = __shfl_sync(0xFFFFFFFFu, f, src & 31u);
         const uint32_t a3 = above ? ent0 + src * 32u + fs : sentinel;
         const uint32_t a2 = mw.w ? mine + 24u : a3;
@@ -448,28 +461,37 @@ __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kerne
         const uint32_t a0 = mw.y ? mine + 8u : a1;
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(mine), "r"(__brev(mw.x)), "r"(a0), "r"(__brev(mw.y)), "r"(a1) : "memory");
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(mine + 16u), "r"(__brev(mw.z)), "r"(a2), "r"(__brev(mw.w)), "r"(a3) : "memory");
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(px0 + lane * 8u), "r"(e | ((e + na) << 16)), "r"((e + nb) | ((e + nc) << 16)) : "memory");
-        if (lane == 0u) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sentinel), "r"(0xFFFFFFFFu), "r"(sentinel) : "memory");
+        sts_u2(px0 + lane * 8u, e | ((e + na) << 16), (e + nb) | ((e + nc) << 16));
+        if (lane == 0u) sts_u2(sentinel, 0xFFFFFFFFu, sentinel);
+        // shares u with e <= u q < e + n start here
+        const uint32_t M = FL2_MAGIC[q];
+        const uint32_t u_hi = ((e + n + q - 1u) * M) >> 20;
+        for (uint32_t u = ((e + q - 1u) * M) >> 20; u < u_hi; u++)
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tab0 + u), "r"(lane) : "memory");
     }
     __syncwarp();
-    // this lane's share: outputs [j0, j0 + q)
-    const uint32_t q = ((Kt + 31u) >> 5) | 1u;
-    const uint32_t j0 = lane * q;
-    // the last word whose exclusive prefix count is <= j0 (word 0 has count 0); among equal counts the last word is the
-    // non-empty one (empty words repeat the count of the non-empty word that follows them)
-    const uint8_t *pp = wbase + Cfg::PX_OFF;
-#pragma unroll
-    for (uint32_t step = 64u; step; step >>= 1)
-        if ((uint32_t)*reinterpret_cast<const uint16_t *>(pp + step * 2u) <= j0) pp += step * 2u;
-    const uint32_t k8 = (uint32_t)(pp - (wbase + Cfg::PX_OFF)) * 4u;          // byte offset of that word's entry
-    const uint2 e = *reinterpret_cast<const uint2 *>(wbase + Cfg::ENT_OFF + k8);
-    const uint32_t r = j0 - (uint32_t)*reinterpret_cast<const uint16_t *>(pp);
-    // the bits of that word that belong to the lanes before this one are dropped; a lane past the end starts used up
-    const bool live = j0 < Kt;
-    const uint32_t w = live ? drop_high_bits(e.x, r) : 0u;
-    const uint32_t vc = c0 * 2048u - P.mis + 31u - 4u * ent0;                 // value base of the entry at address A: 4 A + vc
+    const uint32_t j0 = lane * q;                           // this lane's share: outputs [j0, j0 + q)
+    const bool live = j0 < Kt;                              // (a lane past the end starts used up and only reads the sentinel)
+    uint32_t w = 0u, vb = 0u, nxt = sentinel;
+    if (live) {
+        uint32_t t, rx, ry;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(tab0 + lane) : "memory");
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rx), "=r"(ry) : "r"(px0 + t * 8u) : "memory");
+        // the last of that lane's words whose prefix count is <= j0 (an empty word repeats the count of the word after it)
+        const uint32_t p1 = rx >> 16, p2 = ry & 0xFFFFu, p3 = ry >> 16;
+        uint32_t j = 0u, pj = rx & 0xFFFFu;
+        if (p1 <= j0) { j = 1u; pj = p1; }
+        if (p2 <= j0) { j = 2u; pj = p2; }
+        if (p3 <= j0) { j = 3u; pj = p3; }
+        uint32_t ex, ey;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(ent0 + t * 32u + j * 8u) : "memory");
+        w = drop_high_bits(ex, j0 - pj);                    // the bits that belong to the lanes before this one
+        nxt = ey;
+        vb = c0 * 2048u - P.mis + 31u + t * 128u + j * 32u;
+    }
+    const uint32_t vc = c0 * 2048u - P.mis + 31u - 4u * ent0;   // value base of the entry at address A: 4 A + vc
     const uint32_t a = ((uint32_t)first + out_phase(P.out)) & 3u;
-    flatten_balanced_loop(w, 4u * (ent0 + k8) + vc, live ? e.y : sentinel, smem_u32(stage + a + j0), q, vc);
+    flatten_balanced_loop(w, vb, nxt, smem_u32(stage + a + j0), q, vc);
     __syncwarp();
     copy_out_warp_n<Cfg::NVEC>(stage, a, Kt, P.out, first, P.cap, lane);
 }
