@@ -352,13 +352,13 @@ def kernel_kind_for(args, seg_bytes: int) -> str:
     """Which kernel organisation the library picks for a document of this size (capi.cu: SPLIT_MIN_BYTES / STREAM_MIN_BYTES)."""
     if args.kernel != "auto":
         return args.kernel
-    return "stream" if seg_bytes >= (160 << 20) else "split" if seg_bytes >= (48 << 20) else "persistent"
+    return "stream" if seg_bytes >= (80 << 20) else "split" if seg_bytes >= (24 << 20) else "persistent"
 
 
 KERNEL_NAMES = {
     "stream": "stage-1 stream pipeline, 4 launches per document: stage1_stream_classify_kernel -> stage1_span_scan_kernel -> "
-              "stage1_flatten_kernel (+ stage1_persistent_kernel as a no-op fallback)",
-    "persistent": "stage1_persistent_kernel", "split": "stage1_classify_kernel + stage1_flatten_kernel",
+              "stage1_flatten2_kernel (+ stage1_persistent_kernel as a no-op fallback)",
+    "persistent": "stage1_persistent_kernel", "split": "stage1_classify_kernel + stage1_flatten2_kernel",
 }
 
 

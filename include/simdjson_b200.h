@@ -83,8 +83,8 @@ int32_t sjb200_ctx_set_stream(sjb200_ctx *ctx, void *cuda_stream);
 int32_t sjb200_ctx_set_warps(sjb200_ctx *ctx, int32_t warps);
 /*
  * Force the kernel organisation (tuning / test knob; every choice produces identical results):
- *   AUTO        chosen from the document size: PERSISTENT below 48 MiB and for the chunked host path, SPLIT from 48 MiB,
- *               STREAM from 160 MiB on
+ *   AUTO        chosen from the document size: PERSISTENT below 24 MiB and for the chunked host path, SPLIT from 24 MiB,
+ *               STREAM from 80 MiB on
  *   PERSISTENT  persistent CTAs of compute warps + a scan warp over tiles, classify and flatten of a tile fused, decoupled
  *               look-back between tiles; needs no scratch
  *   SPLIT       two launches: classify (masks + per-chunk carries to L2 / HBM), then flatten

@@ -27,8 +27,8 @@ constexpr uint64_t MIN_TILE = 2 * 2048;
 // for small documents (all 148 SMs get a tile even at a few hundred KiB), the split pair from SPLIT_MIN_BYTES, the stream
 // pipeline from STREAM_MIN_BYTES.  (A fused single-launch organisation and a windowed two-stream pipeline were measured in
 // round 2 and removed again: profiles/r2_overlap_experiments.txt.)
-constexpr uint64_t SPLIT_MIN_BYTES = 48ull << 20;
-constexpr uint64_t STREAM_MIN_BYTES = 160ull << 20;
+constexpr uint64_t SPLIT_MIN_BYTES = 24ull << 20;
+constexpr uint64_t STREAM_MIN_BYTES = 80ull << 20;
 
 inline int32_t cuda_err(cudaError_t e) {
     if (e == cudaSuccess) return SJB200_SUCCESS;
