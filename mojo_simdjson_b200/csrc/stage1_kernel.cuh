@@ -342,7 +342,8 @@ __device__ __forceinline__ void warp_load(LaneInput &in, const uint8_t *smem_til
 #endif
 template <bool UTF8, int DEFER_U8 = 0>
 __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in, int lane, const Stage1Params &P,
-                                             uint4 *u8_slots = nullptr /* DEFER_U8: the warp's free shared-memory slots, 5 uint4 each */) {
+                                             uint4 *u8_slots = nullptr /* DEFER_U8: the warp's free shared-memory slots, 5 uint4 each */,
+                                             uint32_t lt = lanemask_lt() /* bits of the lanes below this one */) {
     LaneMasks m;
     uint32_t u8err = 0;
     r.u8_lanes = 0;
@@ -368,7 +369,7 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
                 // the k-th flagged lane parks its bit planes, the 4 bytes before it and its end-of-document bit in slot k
                 r.u8_lanes = hi_lanes;
                 if (any_hi) {
-                    uint4 *s = u8_slots + 5 * __popc(hi_lanes & lanemask_lt());   // 80 contiguous bytes per slot
+                    uint4 *s = u8_slots + 5 * __popc(hi_lanes & lt);   // 80 contiguous bytes per slot
                     s[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     s[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
                     s[2] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -394,7 +395,6 @@ __device__ __forceinline__ void warp_compute(LanePhase1 &r, const LaneInput &in,
     // A = lanes that are one long backslash run, O = parity of the backslash run each lane ends with; both are zero unless
     // some lane ends in a backslash, which one ballot on the top bit decides
     // Without such a lane no escape crosses a lane boundary: lane 0 inherits the warp's carry, every other lane starts clean.
-    const uint32_t lt = lanemask_lt();
     uint32_t e_in = lane ? 0u : in.wst.e, e_out = 0u;
     if (__ballot_sync(0xFFFFFFFFu, (uint32_t)(m.bs >> 32) >> 31)) {
         const uint32_t bA = __ballot_sync(0xFFFFFFFFu, lane_all_backslash(m.bs));

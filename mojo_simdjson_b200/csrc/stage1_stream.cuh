@@ -246,7 +246,13 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     static_assert(SJ_U8_DEFER_MAX <= 32, "a chunk must not park more lanes than the warp's slots hold");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // lane number and lane mask are read once (volatile: the compiler would otherwise re-derive them from the special
+    // registers inside the loop, a long-latency read in front of dependent instructions each time)
+    int lane;
+    uint32_t lt;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    const int warp = threadIdx.x >> 5;
     uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
     const uint32_t buf0 = smem_u32(wbase);                    // shared-space addresses: 32-bit arithmetic only
     uint8_t *park = wbase + DEPTH * Cfg::BUF;                 // parked UTF-8 lanes of the current run
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
                 if (lane == 0 && held[b] < chunk_end) issue(b, held[b]);
                 if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
                     *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
-                warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked);
+                warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked, lt);
                 parked += (uint32_t)__popc(ph.u8_lanes);
                 prev_c = c;
                 prev_tail = ph.tail;
@@ -408,7 +414,10 @@ __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint
     return a;
 }
 
-constexpr int SPAN_PER_THREAD = 4;                         // consecutive chunk summaries per thread
+#ifndef SJ_SPAN_PER_THREAD
+#define SJ_SPAN_PER_THREAD 4
+#endif
+constexpr int SPAN_PER_THREAD = SJ_SPAN_PER_THREAD;        // consecutive chunk summaries per thread
 constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
 
 // One launch, one CTA per SPAN_BLOCK chunk summaries (8 MiB of input): local ordered reduction -> the block aggregate,
