@@ -214,9 +214,9 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
     // (the first launch of a document is a dependent launch too: back-to-back documents overlap their launch latencies)
-    cudaError_t e = launch_dependent(stage1_stream_classify_kernel<STREAM_NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, pdl, p, nchunks, 0u, nchunks);
+    cudaError_t e = launch_dependent(stage1_stream_classify_kernel<STREAM_NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, pdl, p, nchunks, 0u, nchunks, p.abase - Cfg::HALO);
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
-    if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, 1024, 0, s, pdl, p, nchunks);
+    if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, SPAN_SCAN_THREADS, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_flatten(p, 0u, nchunks, s, pdl);
     c->launches += 3;
     return e;

@@ -240,18 +240,18 @@ __device__ __forceinline__ bool validate_parked_lanes(const uint8_t *park, uint3
 // such a number every later one does too, and no copy is outstanding when the warp leaves.
 template <int NW, bool UTF8>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) stage1_stream_classify_kernel(const Stage1Params P, uint32_t nchunks,
-                                                                                                            uint32_t chunk_begin, uint32_t chunk_end) {
+                                                                                                            uint32_t chunk_begin, uint32_t chunk_end,
+                                                                                                            const uint8_t *src0 /* P.abase - HALO */) {
     using Cfg = StreamCfg<NW>;
     constexpr int DEPTH = Cfg::DEPTH;
     static_assert(SJ_U8_DEFER_MAX <= 32, "a chunk must not park more lanes than the warp's slots hold");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[NW * DEPTH];
-    // lane number and lane mask are read once (volatile: the compiler would otherwise re-derive them from the special
-    // registers inside the loop, a long-latency read in front of dependent instructions each time)
+    // the lane number is read once (volatile: the compiler would otherwise re-derive it from %tid inside the loop, a
+    // long-latency special-register read in front of dependent instructions each time)
     int lane;
-    uint32_t lt;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    const uint32_t lt = lanemask_lt();
     const int warp = threadIdx.x >> 5;
     uint8_t *wbase = smem_raw + warp * Cfg::WARP_BYTES;
     const uint32_t buf0 = smem_u32(wbase);                    // shared-space addresses: 32-bit arithmetic only
@@ -263,12 +263,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
     const uint32_t last_bytes = (uint32_t)(P.alen - (uint64_t)last * 2048u);   // 1 .. 2048
     const uint32_t last_tx = (last_bytes + 15u) & ~15u;                        // stays inside the last 16-byte line of the data
     const bool last_partial = last_bytes < 2048u;
-    const uint8_t *src0 = P.abase - Cfg::HALO;                                 // chunk c with its look-behind starts at src0 + 2048 c
 
     // The first run of every warp is fixed (warp g: chunks 4g .. 4g+3 of the window), so that a launch does not begin with
     // thousands of atomics on one address; the counter hands out the runs after those.  The draw for the run after the
     // current one is always in flight (lane 0 holds its result), so the atomic's latency is never waited for.
     grid_dependency_wait();   // launched while the previous kernel of the stream drains: nothing global is touched before this
+    // (Runs that shrink to single chunks towards the end of the range were measured: no gain, 1 GiB and 64 MiB alike.)
     const uint32_t t_base = chunk_begin + gridDim.x * NW * TICKET_CHUNKS;
     uint32_t t_cur = chunk_begin + (blockIdx.x * NW + warp) * TICKET_CHUNKS, t_left = TICKET_CHUNKS;
     uint32_t drawn = lane == 0 ? ticket_draw(ticket, TICKET_CHUNKS) : 0u;      // lane 0: the run after this one (relative to t_base)
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
         const uint32_t bar = bar0 + 8u * b, dst = buf0 + b * Cfg::BUF;
         if (c - 1u < last - 1u) {   // 0 < c < last: the common case, constant size
             mbar_expect_tx(bar, 2048u + Cfg::HALO);
-            bulk_load(dst, src0 + (size_t)c * 2048u, 2048u + Cfg::HALO, bar);
+            bulk_load(dst, src0 + (size_t)c * 2048u, 2048u + Cfg::HALO, bar);   // src0 = P.abase - HALO
         } else {
             const uint32_t halo = c > 0u ? (uint32_t)Cfg::HALO : 0u;
             const uint32_t tx = (c == last ? last_tx : 2048u) + halo;
@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
 #pragma unroll
     for (int b = 0; b < DEPTH; b++) {
         held[b] = next_chunk();
-        if (lane == 0 && held[b] < chunk_end) issue(b, held[b]);
+        const bool more = held[b] < chunk_end;
+        if (more && lane == 0) issue(b, held[b]);
     }
     uint32_t phase = 0;
     uint32_t parked = 0;           // lanes parked in `park` during the current run
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(StreamCfg<NW>::MAXREG) st
                 chunk_load<UTF8>(in, buf0 + b * Cfg::BUF + Cfg::HALO, lane, c, edge, c == last, last_bytes, P, c == prev_c + 1u, prev_tail, unresolved);
                 __syncwarp();  // every lane has its bytes in registers: the buffer can be refilled
                 held[b] = next_chunk();
-                if (lane == 0 && held[b] < chunk_end) issue(b, held[b]);
+                const bool more = held[b] < chunk_end;   // (decided by all lanes: chunk_end sits in a uniform register)
+                if (more && lane == 0) issue(b, held[b]);
                 if (unresolved && !resolve_long_runs(P, c, unresolved, lane, in.wst) && lane == 0)
                     *P.spec_flag = P.gen;   // someone else has to do this document (see the header)
                 warp_compute<UTF8, 1>(ph, in, lane, P, reinterpret_cast<uint4 *>(park) + 5 * parked, lt);
@@ -396,19 +398,24 @@ __device__ __forceinline__ SpanAcc warp_span_inclusive(SpanAcc a, int lane) {
     }
     return a;
 }
-// inclusive scan over the CTA's 1024 threads in thread order; returns this thread's inclusive span, `total` = the CTA's
+#ifndef SJ_SCAN_THREADS
+#define SJ_SCAN_THREADS 1024
+#endif
+constexpr uint32_t SPAN_SCAN_THREADS = SJ_SCAN_THREADS;
+// inclusive scan over the CTA's threads in thread order; returns this thread's inclusive span, `total` = the CTA's
 __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint4 *s_w /* [32] */, SpanAcc &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARPS = SPAN_SCAN_THREADS / 32;
     SpanAcc a = warp_span_inclusive(mine, lane);
     if (lane == 31) s_w[warp] = make_uint4(a.c[0], a.c[1], span_flags(a), 0u);
     __syncthreads();
     if (warp == 0) {
-        SpanAcc w = warp_span_inclusive(span_from_summary(s_w[lane]), lane);
+        SpanAcc w = warp_span_inclusive(lane < NWARPS ? span_from_summary(s_w[lane]) : span_empty(), lane);
         __syncwarp();
-        s_w[lane] = make_uint4(w.c[0], w.c[1], span_flags(w), 0u);   // inclusive over warps
+        if (lane < NWARPS) s_w[lane] = make_uint4(w.c[0], w.c[1], span_flags(w), 0u);   // inclusive over warps
     }
     __syncthreads();
-    total = span_from_summary(s_w[31]);
+    total = span_from_summary(s_w[NWARPS - 1]);
     if (warp > 0) a = span_concat(span_from_summary(s_w[warp - 1]), a);
     __syncthreads();   // s_w may be reused by the caller
     return a;
@@ -418,14 +425,14 @@ __device__ __forceinline__ SpanAcc block_span_inclusive(const SpanAcc mine, uint
 #define SJ_SPAN_PER_THREAD 4
 #endif
 constexpr int SPAN_PER_THREAD = SJ_SPAN_PER_THREAD;        // consecutive chunk summaries per thread
-constexpr uint32_t SPAN_BLOCK = 1024u * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
+constexpr uint32_t SPAN_BLOCK = SPAN_SCAN_THREADS * SPAN_PER_THREAD;   // chunk summaries per CTA (8 MiB of input)
 
 // One launch, one CTA per SPAN_BLOCK chunk summaries (8 MiB of input): local ordered reduction -> the block aggregate,
 // published with a generation tag -> the aggregates of all earlier blocks (a CTA only ever waits for CTAs with a lower
 // block index, which are resident or finished: CTAs are dispatched in index order) -> one carry word per chunk; the
 // thread that owns the document's last chunk writes the verdict (finish(), reference json_structural_indexer.mojo:147-186).
 // block_sum: 32 bytes per block, {count0, count1, flags, 0} then {generation, 0, 0, 0}.
-__global__ void __launch_bounds__(1024) stage1_span_scan_kernel(const Stage1Params P, uint32_t nchunks) {
+__global__ void __launch_bounds__(SJ_SCAN_THREADS) stage1_span_scan_kernel(const Stage1Params P, uint32_t nchunks) {
     __shared__ uint4 s_w[32];
     grid_dependency_wait();
     if (*reinterpret_cast<volatile uint32_t *>(P.spec_flag) == P.gen) return;
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(1024) stage1_span_scan_kernel(const Stage1Para
     }
     // everything before this block: ordered reduction of the block aggregates 0 .. blk-1 (1024 per round)
     SpanAcc before = span_empty();
-    for (uint32_t b0 = 0; b0 < blk; b0 += 1024u) {
+    for (uint32_t b0 = 0; b0 < blk; b0 += SPAN_SCAN_THREADS) {
         const uint32_t j = b0 + threadIdx.x;
         SpanAcc bj = span_empty();
         if (j < blk) {
