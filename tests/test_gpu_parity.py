@@ -342,6 +342,57 @@ def test_capacity(dev, scratch):
     assert int((scratch.out[100:20000] != -1).sum()) == 0
 
 
+@pytest.mark.parametrize("kernel", ["stream", "split"])
+def test_flatten_units_of_every_density(dev, scratch, kernel):
+    """The balanced flatten kernel works on units of two chunks (4 KiB): every lane extracts the same number of consecutive
+    indexes.  Pieces of very different density side by side -- long strings (no index for kilobytes), one index every few
+    hundred bytes (shares of 1..3 indexes, most mask words empty), the bench document's density, units just below and just
+    above the staging capacity (768 indexes per unit: per-chunk fallback), everything structural -- at piece lengths that
+    are not multiples of a chunk, with an odd number of chunks and with a clipped output capacity."""
+    rng = np.random.default_rng(20261018)
+    pieces = []
+    for rep in range(200):
+        kind = int(rng.choice(9, p=[0.1, 0.15, 0.15, 0.15, 0.15, 0.1, 0.08, 0.06, 0.06]))
+        length = int(rng.integers(300, 9000))
+        if kind == 0:
+            piece = b'"' + b"s" * length + b'",'
+        elif kind == 1:
+            piece = b"".join(b'"' + b"x" * int(rng.integers(100, 700)) + b'",' for _ in range(length // 400 + 1))
+        elif kind == 2:
+            piece = b'"abcdefgh",' * (length // 11 + 1)    # 0.18 per byte: units just below the capacity
+        elif kind == 3:
+            piece = b"12345," * (length // 6 + 1)          # 0.17 per byte
+        elif kind == 4:
+            piece = b"123456789012," * (length // 13 + 1)  # 0.08 per byte
+        elif kind == 5:
+            piece = b'{"id":12345,"text":"hello \\"world\\"","tags":[]},' * (length // 50 + 1)
+        elif kind == 6:
+            piece = b"123,45," * (length // 7 + 1)         # 0.29 per byte: units above the capacity, chunks below 512 + 85
+        elif kind == 7:
+            piece = b"1," * (length // 2 + 1)              # 0.5 per byte
+        else:
+            piece = b"[]," * (length // 3 + 1)             # every byte structural
+        pieces.append(piece)
+    body = b"".join(pieces)
+    for extra in (0, 1777, 2048 + 5):                      # odd / even chunk counts, ragged last chunk
+        data = b"[" + body + b"0" * extra + b"]"
+        want = oracle.stage1(data, impl="fast")
+        assert want.error == 0
+        for mis in (0, 4):
+            res, out = run_device(dev, scratch, data, mis=mis, warps=8, kernel=kernel)
+            assert_same(res, out, want)
+    data = b"[" + body + b"0]"
+    want = oracle.stage1(data, impl="fast")
+    for cap in (want.n + 3, want.n - 1, want.n // 2 + 1, 777):
+        res, out = run_device(dev, scratch, data, cap=cap, warps=8, kernel=kernel)
+        if cap >= want.n + 3:
+            assert_same(res, out, want)
+        else:
+            assert res.error == 1 and res.n is None, cap
+            keep = min(cap, want.n)
+            assert np.array_equal(out[:keep].cpu().numpy().view(np.uint32), want.indexes[:keep]), cap
+
+
 def test_dense_tile_takes_direct_path(dev, scratch):
     data = b"[" + b"1," * 100000 + b"1]"  # every byte structural: > 0.5 per byte, bypasses staging
     want = oracle.stage1(data, impl="fast")
