@@ -14,7 +14,7 @@
 #include "stage1_stream.cuh"
 
 #ifndef SJ_K3_FW
-#define SJ_K3_FW 4   // warps (= chunks) per CTA of the flatten kernel (2 and 4: +0.8 % over 8, 16: -2 %)
+#define SJ_K3_FW 4   // warps (= units of two chunks) per CTA of the flatten kernel (2 and 4 measure alike, 8: -4 %)
 #endif
 
 using namespace sjb200;
@@ -48,7 +48,6 @@ struct Knobs {
     int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
     int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream
     uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
-    int flatten = 2;        // SJB200_FLATTEN=1: the lane-per-word flatten kernel instead of the balanced one (A/B measurements)
 };
 bool valid_warps(int w) { return w == 2 || w == 4 || w == 8 || w == 16 || w == 24; }
 const Knobs &knobs() {
@@ -61,7 +60,6 @@ const Knobs &knobs() {
             if (strcmp(e, "split") == 0) v.kernel = SJB200_KERNEL_SPLIT;
             if (strcmp(e, "stream") == 0) v.kernel = SJB200_KERNEL_STREAM;
         }
-        if (const char *e = getenv("SJB200_FLATTEN")) v.flatten = atoi(e) == 1 ? 1 : 2;
         if (const char *e = getenv("SJB200_CHUNK_MIB"))
             if (atoi(e) > 0) v.chunk_bytes = (uint64_t)atoi(e) << 20;
         return v;
@@ -144,7 +142,6 @@ cudaError_t prepare_persist(int *occ) {
 template <int NW>
 cudaError_t prepare_split(int *occ) {
     using Cfg = SplitCfg<NW>;
-    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_flatten2_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_classify_kernel<NW, true>, stage1_classify_kernel<NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
@@ -157,7 +154,6 @@ cudaError_t prepare_stream(int *occ) {
     // every kernel of the pipeline asks for the same shared-memory carve-out: kernels with different L1 / shared splits
     // cannot share an SM, and scan + flatten of one window must run beside the classify CTAs of the next
     cudaFuncSetAttribute(stage1_span_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(stage1_flatten_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(stage1_flatten2_kernel<SJ_K3_FW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return prepare_kernel(stage1_stream_classify_kernel<STREAM_NW, true>, stage1_stream_classify_kernel<STREAM_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
 }
@@ -185,11 +181,9 @@ cudaError_t launch_persist(const Stage1Params &p, cudaStream_t s, int max_ctas) 
     // as the fallback of the stream pipeline (spec_flag set) it follows the flatten kernel as a dependent launch
     return launch_dependent(stage1_persistent_kernel<NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, p.spec_flag != nullptr && knobs().pdl != 0, p);
 }
-// flatten chunks [c0, c1) (c0 even): the balanced kernel (units of two chunks per warp) or, SJB200_FLATTEN=1, the lane-per-word one
+// flatten chunks [c0, c1) (c0 even): units of two chunks per warp
 cudaError_t launch_flatten(const Stage1Params &p, uint32_t c0, uint32_t c1, cudaStream_t s, bool pdl) {
     constexpr int FW = SJ_K3_FW;
-    if (knobs().flatten == 1)
-        return launch_dependent(stage1_flatten_kernel<FW>, (c1 - c0 + FW * SJ_K3_CPW - 1) / (FW * SJ_K3_CPW), FlattenCfg<FW>::THREADS, FlattenCfg<FW>::SMEM_BYTES, s, pdl, p, c0, c1);
     return launch_dependent(stage1_flatten2_kernel<FW>, (c1 - c0 + FW * 2 - 1) / (FW * 2), Flatten2Cfg<FW>::THREADS, Flatten2Cfg<FW>::SMEM_BYTES, s, pdl, p, c0, c1);
 }
 

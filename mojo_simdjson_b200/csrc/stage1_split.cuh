@@ -13,8 +13,9 @@
 //                            64 input bytes) and moves on.  The scan warp runs the decoupled look-back for every tile
 //                            and leaves, per 2 KiB chunk, one 8-byte carry word: bit 63 = chunk starts inside a string,
 //                            bits 0..39 = rank of its first structural in the output.  It also writes the verdict.
-//   stage1_flatten_kernel  : one warp per chunk, no shared state between warps: carry word -> pick the mask plane ->
-//                            popcount, warp scan, extract into the warp's staging area, 16-byte stores.
+//   stage1_flatten2_kernel : one warp per unit of two chunks, no shared state between warps: carry word -> pick the mask
+//                            plane -> every lane extracts the same number of consecutive indexes (balanced, see below)
+//                            into the warp's staging area, 16-byte stores.
 //
 // Extra HBM traffic: the mask planes, 16 B written + 8 B read per 64 input bytes (+23 % over the algorithmic bytes at the
 // bench document's density of 0.161 structurals per byte).
@@ -213,19 +214,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) __maxnreg__(SplitCfg<NW>::MAXRE
     }
 }
 
-#ifndef SJ_K3_MINCTAS
-#define SJ_K3_MINCTAS 8   // resident CTAs per SM the flatten kernel's register budget allows (8 -> 32 registers)
-#endif
-
-template <int FW>
-struct FlattenCfg {
-    static constexpr int THREADS = FW * 32;
-    static constexpr int WCAP = 512;
-    static constexpr int SMEM_BYTES = FW * (WCAP + 4) * 4;
-};
-
-// one warp flattens chunk c: carry word -> plane -> popcount, warp scan, extraction into `stage` (the warp's staging area
-// of WCAP + 4 entries in shared memory), 16-byte stores.  BitIndexer.write, reference json_structural_indexer.mojo:46-58.
+// one warp flattens chunk c, every lane its own 64-bit mask word (the balanced kernel's path for units denser than its staging
+// area): carry word -> plane -> popcount, warp scan, extraction into `stage` (the warp's staging area of WCAP + 4 entries in
+// shared memory), 16-byte stores.  BitIndexer.write, reference json_structural_indexer.mojo:46-58.
 template <int WCAP>
 __device__ __forceinline__ void flatten_chunk(const Stage1Params &P, uint32_t c, uint64_t carry, uint64_t structural, uint32_t *stage, int lane) {
     const uint64_t first = carry & CARRY_RANK_MASK;
@@ -246,45 +237,9 @@ __device__ __forceinline__ void flatten_chunk(const Stage1Params &P, uint32_t c,
     }
 }
 
-#ifndef SJ_K3_CPW
-#define SJ_K3_CPW 2   // consecutive chunks per warp of the flatten kernel: carries and mask words of all of them are requested up front
-#endif
-
-// chunks [chunk_begin, chunk_end): SJ_K3_CPW consecutive chunks per warp
-template <int FW>
-__global__ void __launch_bounds__(FW * 32, SJ_K3_MINCTAS * 8 / FW) stage1_flatten_kernel(const Stage1Params P, uint32_t chunk_begin, uint32_t chunk_end) {
-    using Cfg = FlattenCfg<FW>;
-    constexpr uint32_t CPW = SJ_K3_CPW;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw) + warp * (Cfg::WCAP + 4);
-    const uint32_t c0 = chunk_begin + (blockIdx.x * FW + warp) * CPW;
-    grid_dependency_wait();
-    if (c0 >= chunk_end) return;
-    const uint32_t gave_up = P.spec_flag ? __ldcg(P.spec_flag) : 0u;   // stream pipeline only; loaded together with the carries
-    uint64_t carry[CPW], structural[CPW];
-#pragma unroll
-    for (uint32_t j = 0; j < CPW; j++)
-        carry[j] = c0 + j < chunk_end ? __ldcg(reinterpret_cast<const unsigned long long *>(P.carry + c0 + j)) : 0ull;
-    if (P.spec_flag && gave_up == P.gen) return;
-#pragma unroll
-    for (uint32_t j = 0; j < CPW; j++) {
-        const uint32_t s_w = (uint32_t)(carry[j] >> 63);
-        structural[j] = c0 + j < chunk_end ? __ldcs(reinterpret_cast<const unsigned long long *>(P.masks + (size_t)(c0 + j) * 64 + s_w * 32 + lane)) : 0ull;
-    }
-#pragma unroll
-    for (uint32_t j = 0; j < CPW; j++) {
-        if (c0 + j < chunk_end) {
-            flatten_chunk<Cfg::WCAP>(P, c0 + j, carry[j], structural[j], stage, lane);
-            if (j + 1 < CPW) __syncwarp();   // the staging area is reused by the next chunk
-        }
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// Balanced flatten.  stage1_flatten_kernel gives every lane the 64 bits of its own mask word: the extraction loop then
-// runs max-over-lanes trips (27.5 per chunk on the bench document for 10.3 indexes per lane on average -- 39 % of the
+// Balanced flatten.  Giving every lane the 64 bits of its own mask word (flatten_chunk above; the whole kernel until the
+// second half of round 2) makes the extraction loop run max-over-lanes trips (27.5 per chunk on the bench document for 10.3 indexes per lane on average -- 39 % of the
 // lanes do useful work).  Here a warp takes a UNIT of two consecutive chunks (4 KiB of input, ~660 indexes; lane t holds the
 // four 32-bit mask words of bytes [128 t, 128 t + 128)), and every lane extracts the SAME number q = ceil(K / 32) of
 // consecutive indexes of the unit's output:

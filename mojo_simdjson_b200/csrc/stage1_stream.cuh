@@ -11,7 +11,7 @@
 //   span_scan       : one CTA per 4096 chunk summaries: ordered (non-commutative span_concat) local reduction -> block
 //                     aggregate, published; the aggregates of the earlier blocks -> one carry word per chunk (bit 63 =
 //                     starts inside a string, bits 0..39 = rank of its first index) and the verdict.
-//   flatten         : stage1_flatten_kernel (stage1_split.cuh), one warp per chunk.
+//   flatten         : stage1_flatten2_kernel (stage1_split.cuh), one warp per unit of two chunks.
 //
 // The carries a 32-byte look-behind cannot decide are the escape state after a backslash run that covers all of it and the
 // scalar state after a quote preceded by 31 backslashes.  A chunk that sees either walks back through global memory
