@@ -250,27 +250,32 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(WideCfg<NW>::MAXREG) stag
         const uint64_t pot_a = ma.op | (scalar_a & ~((nqs_a << 1) | p_in));
         const uint64_t pot_b = mb.op | (scalar_b & ~((nqs_b << 1) | (nqs_a >> 63)));
         const uint64_t tail_a = in0_a ^ quote_a, tail_b = in0_b ^ quote_b;
-        const uint64_t m0a = pot_a & ~tail_a, m1a = pot_a & tail_a, m0b = pot_b & ~tail_b, m1b = pot_b & tail_b;
-        const uint32_t un0 = ((ma.ctl & in0_a) | (mb.ctl & in0_b)) != 0, un1 = ((ma.ctl & ~in0_a) | (mb.ctl & ~in0_b)) != 0;
-        const uint32_t c0 = (uint32_t)(__popcll(m0a) + __popcll(m0b)), c1 = (uint32_t)(__popcll(m1a) + __popcll(m1b));
+        uint64_t m0a = pot_a & ~tail_a, m1a = pot_a & tail_a, m0b = pot_b & ~tail_b, m1b = pot_b & tail_b;
+        uint32_t un0 = ((ma.ctl & in0_a) | (mb.ctl & in0_b)) != 0, un1 = ((ma.ctl & ~in0_a) | (mb.ctl & ~in0_b)) != 0;
+        uint32_t c0 = (uint32_t)(__popcll(m0a) + __popcll(m0b)), c1 = (uint32_t)(__popcll(m1a) + __popcll(m1b));
         // ---- per-chunk results: lanes 0..15 are chunk c, lanes 16..31 chunk c + 1, whose own "starts outside a string" is the
-        // unit's "starts inside" when chunk c holds an odd number of quotes: those lanes exchange the roles of their two planes,
-        // counts and flags (the values stay where they are, the places they go to are swapped)
+        // unit's "starts inside" when chunk c holds an odd number of quotes
         const uint32_t par0 = (uint32_t)__popc(bPB & 0xFFFFu) & 1u;    // parity of chunk c's quotes
         const uint32_t par1 = ((uint32_t)__popc(bPB) & 1u) ^ par0;     // parity of chunk c + 1's
-        const bool swap = (lane_chunk & par0) != 0u;
-        const uint32_t pack = swap ? (c1 | (c0 << 16)) : (c0 | (c1 << 16));   // a chunk holds at most 2048 indexes
+        if (lane_chunk & par0) {   // second chunk, string state flipped by the first one
+            uint64_t t;
+            t = m0a; m0a = m1a; m1a = t;
+            t = m0b; m0b = m1b; m1b = t;
+            uint32_t s;
+            s = c0; c0 = c1; c1 = s;
+            s = un0; un0 = un1; un1 = s;
+        }
+        const uint32_t pack = c0 | (c1 << 16);                         // a chunk holds at most 2048 indexes
         const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, pack);
         const uint32_t first = __reduce_add_sync(0xFFFFFFFFu, lane_chunk ? 0u : pack);
         const uint32_t second = tot - first;
-        const uint32_t fl = (swap ? (un1 << 1) | (un0 << 2) : (un0 << 1) | (un1 << 2)) | (u8err << 3);
+        const uint32_t fl = (un0 << 1) | (un1 << 2) | (u8err << 3);
         const uint32_t flags_all = __reduce_or_sync(0xFFFFFFFFu, lane_chunk ? fl << 8 : fl);
         // stores: both planes of this lane's chunk ([chunk][parity][lane], this lane's two words are words 2 (lane & 15), + 1)
         if (lane_chunk == 0u || two) {
             uint64_t *mp = P.masks + (size_t)(c + lane_chunk) * 64 + 2u * ((uint32_t)lane & 15u);
-            uint64_t *mp0 = swap ? mp + 32 : mp, *mp1 = swap ? mp : mp + 32;
-            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(mp0), "l"(m0a), "l"(m0b) : "memory");
-            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(mp1), "l"(m1a), "l"(m1b) : "memory");
+            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(mp), "l"(m0a), "l"(m0b) : "memory");
+            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(mp + 32), "l"(m1a), "l"(m1b) : "memory");
         }
         if (lane == 0) reinterpret_cast<uint4 *>(P.chunk_sum)[c] = make_uint4(first & 0xFFFFu, first >> 16, (flags_all & 0xFFu) | par0, 0u);
         if (lane == 16 && two) reinterpret_cast<uint4 *>(P.chunk_sum)[c + 1u] = make_uint4(second & 0xFFFFu, second >> 16, ((flags_all >> 8) & 0xFFu) | par1, 0u);

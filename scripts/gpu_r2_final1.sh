@@ -11,7 +11,6 @@ done
 timeout 300 python bench.py --no-utf8 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_final_noutf8.log 2>&1; echo "noutf8 rc=$?"; tail -1 gpurun_out/bench_final_noutf8.log | cut -c1-160
 timeout 300 python bench.py --kernel persistent --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/bench_final_persistent.log 2>&1; echo "persistent rc=$?"; tail -1 gpurun_out/bench_final_persistent.log | cut -c1-160
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_final_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_final_ref.log | cut -c1-200
-SJB200_WIDE=0 KERNELS=stream timeout 300 python tools/quickbench.py 1024 2>&1 | tail -1 > gpurun_out/narrow_final.log; cat gpurun_out/narrow_final.log
 KERNELS=auto,persistent,split,stream SIZES=1,4,16,32,64,128,256,512,1024 timeout 600 python tools/sizesweep.py > gpurun_out/sizesweep_final.log 2>&1; cat gpurun_out/sizesweep_final.log
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_list_final.log 2>&1; echo "list rc=$?"
