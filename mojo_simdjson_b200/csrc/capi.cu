@@ -12,7 +12,6 @@
 #include "stage1_persistent.cuh"
 #include "stage1_split.cuh"
 #include "stage1_stream.cuh"
-#include "stage1_stream2.cuh"
 
 #ifndef SJ_K3_FW
 #define SJ_K3_FW 4   // warps (= units of two chunks) per CTA of the flatten kernel (2 and 4 measure alike, 8: -4 %)
@@ -46,7 +45,6 @@ inline int32_t cuda_err(cudaError_t e) {
 // Tuning knobs from the environment, read ONCE (first context creation), never on the call path.
 struct Knobs {
     int pdl = 1;            // SJB200_PDL=0: no programmatic dependent launch between the launches of a document
-    int wide = 1;           // SJB200_WIDE=0: always the 64-byte-lane classify kernel (A/B measurements)
     int warps = 0;          // SJB200_WARPS: tile shape of the persistent kernel (2/4/8/16/24)
     int kernel = SJB200_KERNEL_AUTO;   // SJB200_KERNEL=persist|split|stream
     uint64_t chunk_bytes = 32ull << 20;   // SJB200_CHUNK_MIB: chunk size of the streaming host path
@@ -56,7 +54,6 @@ const Knobs &knobs() {
     static const Knobs k = [] {
         Knobs v;
         if (const char *e = getenv("SJB200_PDL")) v.pdl = atoi(e);
-        if (const char *e = getenv("SJB200_WIDE")) v.wide = atoi(e) != 0;
         if (const char *e = getenv("SJB200_WARPS")) v.warps = valid_warps(atoi(e)) ? atoi(e) : 0;
         if (const char *e = getenv("SJB200_KERNEL")) {
             if (strcmp(e, "persist") == 0) v.kernel = SJB200_KERNEL_PERSISTENT;
@@ -94,7 +91,6 @@ struct sjb200_ctx {
     int persist_occ[5] = {0, 0, 0, 0, 0};  // resident CTAs per SM of the persistent kernel for NW = 2, 4, 8, 16, 24
     int split_occ[2] = {0, 0};             // same for the classify kernel of the split pair, NW = 8, 16
     int stream_occ = 0;                    // same for the stream classify kernel
-    int wide_occ = 0;                      // same for the 128-byte-lane classify kernel
     // scratch of the split / stream organisations, sized for `scratch_chunks` 2 KiB chunks (sjb200_ctx_reserve, or
     // grown on demand with the stream-ordered allocator: no call ever synchronises for it)
     uint64_t *d_masks = nullptr;           // the two structural mask planes of every chunk (512 B per chunk)
@@ -191,37 +187,6 @@ cudaError_t launch_flatten(const Stage1Params &p, uint32_t c0, uint32_t c1, cuda
     return launch_dependent(stage1_flatten2_kernel<FW>, (c1 - c0 + FW * 2 - 1) / (FW * 2), Flatten2Cfg<FW>::THREADS, Flatten2Cfg<FW>::SMEM_BYTES, s, pdl, p, c0, c1);
 }
 
-constexpr int WIDE_NW = SJ_WIDE_NW;
-cudaError_t prepare_wide(int *occ) {
-    using Cfg = WideCfg<WIDE_NW>;
-    return prepare_kernel(stage1_stream_classify2_kernel<WIDE_NW, true>, stage1_stream_classify2_kernel<WIDE_NW, false>, Cfg::THREADS, Cfg::SMEM_BYTES, occ);
-}
-// The tensor-map encoder of the driver, fetched through the runtime (no link against libcuda); null if it is not there.
-typedef CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-TensorMapEncodeTiled tensor_map_encoder() {
-    static const TensorMapEncodeTiled fn = [] {
-        void *f = nullptr;
-        cudaDriverEntryPointQueryResult st;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) f = nullptr;
-        cudaGetLastError();
-        return reinterpret_cast<TensorMapEncodeTiled>(f);
-    }();
-    return fn;
-}
-// The document as rows of 128 bytes, fetched 32 rows (one unit of two chunks) at a time with the 128-byte swizzle.  False if it
-// cannot be had: no encoder, or the document does not start on a 128-byte boundary (the last row of a copy must stay inside
-// the last 128-byte line of the data).
-bool encode_document_map(CUtensorMap *tm, const uint8_t *abase, uint64_t alen) {
-    const TensorMapEncodeTiled enc = tensor_map_encoder();
-    if (!enc || (reinterpret_cast<uintptr_t>(abase) & 127u) != 0 || knobs().wide == 0) return false;
-    const cuuint64_t gdim[2] = {128, (alen + 127) / 128};
-    const cuuint64_t gstr[1] = {128};
-    const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(abase), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int NW, bool UTF8>
 cudaError_t launch_split(const Stage1Params &p, cudaStream_t s, int max_ctas) {
     using Cfg = SplitCfg<NW>;
@@ -243,16 +208,7 @@ cudaError_t launch_stream(sjb200_ctx *c, const Stage1Params &p, cudaStream_t s, 
     const unsigned want = (nchunks + STREAM_NW - 1) / STREAM_NW;
     const unsigned grid = want < (unsigned)max_ctas ? want : (unsigned)max_ctas;
     // (the first launch of a document is a dependent launch too: back-to-back documents overlap their launch latencies)
-    cudaError_t e;
-    CUtensorMap tm;
-    if (encode_document_map(&tm, p.abase, p.alen)) {   // lanes of 128 bytes on a swizzled layout (stage1_stream2.cuh)
-        using Wide = WideCfg<WIDE_NW>;
-        const unsigned wwant = ((nchunks + 1) / 2 + WIDE_NW - 1) / WIDE_NW, wmax = (unsigned)(c->sm_count * c->wide_occ);
-        e = launch_dependent(stage1_stream_classify2_kernel<WIDE_NW, UTF8>, wwant < wmax ? wwant : wmax, Wide::THREADS, Wide::SMEM_BYTES, s, pdl, p, nchunks,
-                             p.abase - Wide::HALO, tm);
-    } else {
-        e = launch_dependent(stage1_stream_classify_kernel<STREAM_NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, pdl, p, nchunks, 0u, nchunks, p.abase - Cfg::HALO);
-    }
+    cudaError_t e = launch_dependent(stage1_stream_classify_kernel<STREAM_NW, UTF8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, pdl, p, nchunks, 0u, nchunks, p.abase - Cfg::HALO);
     const unsigned nblocks = (nchunks + SPAN_BLOCK - 1) / SPAN_BLOCK;
     if (e == cudaSuccess) e = launch_dependent(stage1_span_scan_kernel, nblocks, SPAN_SCAN_THREADS, 0, s, pdl, p, nchunks);
     if (e == cudaSuccess) e = launch_flatten(p, 0u, nchunks, s, pdl);
@@ -680,7 +636,6 @@ int32_t sjb200_ctx_create(int32_t device, uint64_t max_len, uint64_t max_len_hos
     if (e == cudaSuccess) e = prepare_split<8>(&c->split_occ[0]);
     if (e == cudaSuccess) e = prepare_split<16>(&c->split_occ[1]);
     if (e == cudaSuccess) e = prepare_stream(&c->stream_occ);
-    if (e == cudaSuccess) e = prepare_wide(&c->wide_occ);
     if (e == cudaSuccess) {
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
