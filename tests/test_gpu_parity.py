@@ -317,6 +317,29 @@ def test_every_misalignment(dev, scratch):
         assert_same(res, out, want)
 
 
+def test_stream_pipeline_at_every_start_in_a_line(dev, scratch):
+    """The stream pipeline on documents that start anywhere inside a 128-byte line (a variant of its classify kernel with
+    128-byte lanes on a swizzled layout, tried in round 2, depended on that; the test stayed): non-ASCII text in most lanes,
+    an odd number of chunks, invalid UTF-8 in the middle and as the last bytes of a unit / an odd chunk."""
+    from mojo_simdjson_b200 import synth
+    docs = [c[1] for c in cases.adversarial_cases()][:40]
+    docs.append(b'{"k":"v\\"x","a":[1,2,3],"u":"\xe2\x82\xac \xf0\x9f\x98\x80"}' * 4000)       # ~100 chunks, non-ASCII in most lanes
+    docs.append(b"[" + b'"\xe4\xb8\xad\xe6\x96\x87 text \\\\ \\" end",' * 9000 + b"0]")
+    docs.append(bytes(synth.status_array((3 << 20) + 4097)))                                      # odd number of chunks, ragged end
+    bad = docs[-3]
+    docs.append(bad[:70001] + b"\xe2\x82" + bad[70001:])      # a truncated sequence in the middle: UTF8_ERROR
+    docs.append(bad[:4096 * 9 - 1] + b"\xc3")                  # ... and as the very last byte, right at the end of a unit
+    docs.append(bad[:4096 * 9 + 2047] + b"\xf0\x9f")           # ... and at the end of an odd chunk
+    for data in docs:
+        want = oracle.stage1(data, impl="fast", flags=oracle.FLAG_VALIDATE_UTF8)
+        for mis in (0, 5, 16, 64 + 3, 112, 127):
+            res, out = run_device(dev, scratch, data, mis=mis, flags=oracle.FLAG_VALIDATE_UTF8, warps=8, kernel="stream")
+            try:
+                assert_same(res, out, want)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"len={len(data)} mis={mis}") from e
+
+
 def test_flags(dev, scratch):
     bad = b'["\xc0\x80"]' * 10
     res, _ = run_device(dev, scratch, bad, flags=1)
