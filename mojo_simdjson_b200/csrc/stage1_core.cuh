@@ -436,6 +436,31 @@ SJ_HD LaneDual lane_structurals_dual(const LaneMasks &m, const LaneQuotes &q, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// Arithmetic of the balanced flatten kernel (stage1_split.cuh: stage1_flatten2_kernel), shared with the host emulator.
+// ------------------------------------------------------------------------------------------------
+// floor(x / q) = (x * FL2_MAGIC_VALUES[q]) >> 20 for 0 < q < 64 and x <= 34 q, x < 4200 (32-bit product; the kernel divides
+// prefix counts of a unit of at most 32 q indexes; tests/test_core_emulation.py checks every pair)
+#define SJ_FL2_MAGIC_VALUES 0, 1048577, 524289, 349526, 262145, 209716, 174763, 149797, 131073, 116509, 104858, 95326, 87382, 80660, 74899, 69906, 65537, 61681, 58255, 55189, 52429, 49933, 47663, 45591, 43691, 41944, 40330, 38837, 37450, 36158, 34953, 33826, 32769, 31776, 30841, 29960, 29128, 28340, 27595, 26887, 26215, 25576, 24967, 24386, 23832, 23302, 22796, 22311, 21846, 21400, 20972, 20561, 20165, 19785, 19419, 19066, 18725, 18397, 18079, 17773, 17477, 17190, 16913, 16645
+SJ_HD uint32_t fl2_div(uint32_t x, uint32_t magic) { return (x * magic) >> 20; }
+// every lane's share of a unit of K indexes: q consecutive outputs, q odd (the staging stores of the 32 lanes, stride q, then
+// never share a bank)
+SJ_HD uint32_t fl2_share(uint32_t K) { return ((K + 31u) >> 5) | 1u; }
+// w (bit-reversed mask word) without its r highest set bits, r < popc(w): a binary descent to the largest `pos` whose top
+// `pos` bits hold exactly r set bits
+SJ_HD uint32_t drop_high_bits(uint32_t w, uint32_t r) {
+    uint32_t ws = w, pos = 0;   // ws = w << pos
+    for (int s = 16; s; s >>= 1) {
+        const uint32_t c = (uint32_t)popc32(ws >> (32 - s));   // set bits among the next s bits from the top
+        if (c <= r) {
+            r -= c;
+            ws <<= s;
+            pos += s;
+        }
+    }
+    return w & (0xFFFFFFFFu >> pos);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tile descriptors for the single-pass look-back (one 64-bit word per tile, generation tagged).
 //   AGG    : what the tile contributes, for both values of "the tile starts inside a string"
 //   PREFIX : the state after the tile and the number of indexes produced up to and including it

@@ -280,8 +280,7 @@ struct Flatten2Cfg {
     static_assert(STAGE >= 512 + 4, "the per-chunk fallback stages up to 512 indexes");
     static_assert(STAGE_OFF % 16 == 0 && PX_OFF % 16 == 0, "16-byte vectors");
 };
-// floor(x / q) = (x * FL2_MAGIC[q]) >> 20 for x < 4200, q < 64 (checked exhaustively when the table was generated)
-__constant__ uint32_t FL2_MAGIC[64] = {0, 1048577, 524289, 349526, 262145, 209716, 174763, 149797, 131073, 116509, 104858, 95326, 87382, 80660, 74899, 69906, 65537, 61681, 58255, 55189, 52429, 49933, 47663, 45591, 43691, 41944, 40330, 38837, 37450, 36158, 34953, 33826, 32769, 31776, 30841, 29960, 29128, 28340, 27595, 26887, 26215, 25576, 24967, 24386, 23832, 23302, 22796, 22311, 21846, 21400, 20972, 20561, 20165, 19785, 19419, 19066, 18725, 18397, 18079, 17773, 17477, 17190, 16913, 16645};
+__constant__ uint32_t FL2_MAGIC[64] = {SJ_FL2_MAGIC_VALUES};   // floor(x / q) = fl2_div(x, FL2_MAGIC[q]), stage1_core.cuh
 
 // q trips of the balanced extraction loop (q >= 1, warp-uniform).  w: current word (bit-reversed; may be 0 = used up), vb: the
 // index value of its bit 31, na: shared-memory address of the next non-empty entry {word, address of the one after it} (the
@@ -310,22 +309,6 @@ __device__ __forceinline__ void flatten_balanced_loop(uint32_t w, uint32_t vb, u
         : "+r"(w), "+r"(vb), "+r"(na), "+r"(sp)
         : "r"(q), "r"(vc)
         : "memory");
-}
-
-// w (bit-reversed mask word) without its r highest set bits, r < popc(w): a binary descent to the largest `pos` whose top
-// `pos` bits hold exactly r set bits
-__device__ __forceinline__ uint32_t drop_high_bits(uint32_t w, uint32_t r) {
-    uint32_t ws = w, pos = 0;   // ws = w << pos
-#pragma unroll
-    for (int s = 16; s; s >>= 1) {
-        const uint32_t c = (uint32_t)__popc(ws >> (32 - s));   // set bits among the next s bits from the top
-        if (c <= r) {
-            r -= c;
-            ws <<= s;
-            pos += s;
-        }
-    }
-    return w & (0xFFFFFFFFu >> pos);
 }
 
 // stage[a .. a+total) -> out[first .. first+total) by one warp, total <= 4 * NV - 6: NV predicated 16-byte copies per lane
@@ -400,7 +383,7 @@ __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kerne
     }
     if (Kt == 0u) return;
     const uint32_t sentinel = ent0 + 1024u;
-    const uint32_t q = ((Kt + 31u) >> 5) | 1u;             // every lane's share: q consecutive outputs (odd: conflict-free staging stores)
+    const uint32_t q = fl2_share(Kt);                       // every lane's share: q consecutive outputs (odd: conflict-free staging stores)
     {   // this lane's four entries, their prefix counts, and the lanes whose share starts inside its 128 bytes
         const uint32_t e = incl - n;
         const uint32_t mine = ent0 + lane * 32u;
@@ -420,8 +403,8 @@ __global__ void __launch_bounds__(FW * 32, SJ_FL2_MINCTAS) stage1_flatten2_kerne
         if (lane == 0u) sts_u2(sentinel, 0xFFFFFFFFu, sentinel);
         // shares u with e <= u q < e + n start here
         const uint32_t M = FL2_MAGIC[q];
-        const uint32_t u_hi = ((e + n + q - 1u) * M) >> 20;
-        for (uint32_t u = ((e + q - 1u) * M) >> 20; u < u_hi; u++)
+        const uint32_t u_hi = fl2_div(e + n + q - 1u, M);
+        for (uint32_t u = fl2_div(e + q - 1u, M); u < u_hi; u++)
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(tab0 + u), "r"(lane) : "memory");
     }
     __syncwarp();

@@ -27,6 +27,12 @@ def lib():
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint32]
         L.emu_bitplanes32.restype = None
         L.emu_bitplanes32.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_fl2_div.restype = C.c_uint32
+        L.emu_fl2_div.argtypes = [C.c_uint32, C.c_uint32]
+        L.emu_drop_high_bits.restype = C.c_uint32
+        L.emu_drop_high_bits.argtypes = [C.c_uint32, C.c_uint32]
+        L.emu_flatten_unit.restype = C.c_int32
+        L.emu_flatten_unit.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -65,3 +71,14 @@ def stage1_stream(data: bytes, mis: int = 0, flags: int = 0, cap=None):
     assigned = n.value != 0xFFFFFFFF
     keep = min(int(nw.value) + (3 if assigned else 0), cap)
     return err, (n.value if assigned else None), int(nw.value), out[:keep].copy(), int(u8.value), bool(spec.value)
+
+
+def flatten_unit(words: np.ndarray, value_base: int = 0, cap: int = 768):
+    """The balanced flatten kernel's steps for one unit of 128 mask words.  Returns (rc, indexes)."""
+    L = lib()
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    assert w.size == 128
+    out = np.zeros(4096, dtype=np.uint32)
+    count = C.c_uint32(0)
+    rc = L.emu_flatten_unit(w.ctypes.data, value_base, cap, out.ctypes.data, C.byref(count))
+    return rc, out[: count.value].copy()

@@ -540,3 +540,104 @@ extern "C" int32_t emu_stage1_stream(const uint8_t *buf, uint64_t len, uint32_t 
     if ((flags & 1u) && (fin.err & EF_UTF8)) return 11;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Balanced flatten of one unit (csrc/stage1_split.cuh: stage1_flatten2_kernel) on the host: 128 mask words in stream order
+// (lane t owns words 4t .. 4t+3), every lane extracts the same number q of consecutive indexes.  Same steps as the kernel:
+// entries {word bit-reversed, next non-empty entry}, prefix counts, the table "share u starts in lane t" filled by the word
+// owners with the division-by-multiplication, the start word from the owner's four prefix counts, drop_high_bits, q trips of
+// {next entry if the word is used up; find, clear, subtract, store}.  Returns 1 if the unit is denser than the staging
+// capacity (the kernel then flattens it chunk by chunk), else 0 with the unit's indexes in out[0 .. *count).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+uint32_t brev32(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+}
+}  // namespace
+
+extern "C" uint32_t emu_fl2_div(uint32_t x, uint32_t q) {
+    static const uint32_t MAGIC[64] = {SJ_FL2_MAGIC_VALUES};
+    return fl2_div(x, MAGIC[q]);
+}
+extern "C" uint32_t emu_drop_high_bits(uint32_t w, uint32_t r) { return drop_high_bits(w, r); }
+
+extern "C" int32_t emu_flatten_unit(const uint32_t *w, uint32_t value_base, uint32_t cap_indexes, uint32_t *out, uint32_t *count) {
+    static const uint32_t MAGIC[64] = {SJ_FL2_MAGIC_VALUES};
+    const uint32_t SENTINEL = 128;
+    uint32_t n[32], e[32], px[128], wrev[129], next[129];
+    uint32_t K = 0;
+    for (int t = 0; t < 32; t++) {
+        e[t] = K;
+        n[t] = 0;
+        for (int j = 0; j < 4; j++) {
+            px[4 * t + j] = K;
+            K += (uint32_t)popc32(w[4 * t + j]);
+        }
+        n[t] = K - e[t];
+    }
+    *count = K;
+    if (K > cap_indexes) return 1;
+    if (K == 0) return 0;
+    // entries: the word owners link the non-empty words (within the lane, then to the first one of the next lane that has any)
+    for (int t = 0; t < 32; t++) {
+        uint32_t after = SENTINEL;
+        for (int s = t + 1; s < 32 && after == SENTINEL; s++)
+            for (int j = 0; j < 4; j++)
+                if (w[4 * s + j]) {
+                    after = (uint32_t)(4 * s + j);
+                    break;
+                }
+        uint32_t nx = after;
+        for (int j = 3; j >= 0; j--) {
+            wrev[4 * t + j] = brev32(w[4 * t + j]);
+            next[4 * t + j] = nx;
+            if (w[4 * t + j]) nx = (uint32_t)(4 * t + j);
+        }
+    }
+    wrev[SENTINEL] = 0xFFFFFFFFu;
+    next[SENTINEL] = SENTINEL;
+    const uint32_t q = fl2_share(K);
+    uint32_t tab[32];
+    for (int u = 0; u < 32; u++) tab[u] = 0xFFFFFFFFu;
+    for (int t = 0; t < 32; t++) {
+        const uint32_t u_hi = fl2_div(e[t] + n[t] + q - 1u, MAGIC[q]);
+        for (uint32_t u = fl2_div(e[t] + q - 1u, MAGIC[q]); u < u_hi; u++) {
+            if (u >= 32 || tab[u] != 0xFFFFFFFFu) return -1;   // every share is claimed exactly once
+            tab[u] = (uint32_t)t;
+        }
+    }
+    std::vector<uint32_t> stage(32 * q, 0xFFFFFFFFu);
+    for (uint32_t u = 0; u < 32; u++) {
+        const uint32_t j0 = u * q;
+        uint32_t cur = 0, vb = 0, nxt = SENTINEL;
+        if (j0 < K) {
+            const uint32_t t = tab[u];
+            if (t >= 32) return -2;
+            uint32_t j = 0;
+            for (uint32_t i = 1; i < 4; i++)
+                if (px[4 * t + i] <= j0) j = i;
+            const uint32_t k = 4 * t + j;
+            if (j0 - px[k] >= (uint32_t)popc32(w[k])) return -3;   // the start word holds output j0
+            cur = drop_high_bits(wrev[k], j0 - px[k]);
+            nxt = next[k];
+            vb = value_base + 32u * k + 31u;
+        }
+        for (uint32_t trip = 0; trip < q; trip++) {
+            if (cur == 0) {
+                const uint32_t k = nxt;
+                cur = wrev[k];
+                nxt = next[k];
+                vb = value_base + 32u * k + 31u;
+            }
+            const uint32_t h = 31u - (uint32_t)clz32(cur);
+            cur ^= 1u << h;
+            stage[j0 + trip] = vb - h;
+        }
+    }
+    for (uint32_t i = 0; i < K; i++) out[i] = stage[i];
+    return 0;
+}

@@ -127,3 +127,64 @@ def test_stream_pipeline_many_blocks():
 @given(st.lists(st.sampled_from(list(cases.NASTY)), min_size=1, max_size=9000), st.integers(0, 15))
 def test_stream_pipeline_fuzz_nasty(xs, mis):
     _check_stream(bytes(xs), mis)
+
+
+# ------------------------------------------------------------------------------------------------
+# balanced flatten kernel (stage1_split.cuh: stage1_flatten2_kernel): its arithmetic and its steps for one unit
+# ------------------------------------------------------------------------------------------------
+def test_flatten_division_by_multiplication_is_exact():
+    L = emu.lib()
+    # the kernel divides x = (prefix count + q - 1) <= K + q - 1 by q, with K <= 32 q indexes in the unit (32-bit products)
+    for q in range(1, 64):
+        for x in range(0, min(4200, 34 * q + 2)):
+            assert L.emu_fl2_div(x, q) == x // q, (x, q)
+
+
+def test_flatten_drop_high_bits():
+    rng = random.Random(11)
+    L = emu.lib()
+    for _ in range(4000):
+        w = rng.getrandbits(32) & rng.getrandbits(32) if rng.random() < 0.5 else rng.getrandbits(32)
+        if w == 0:
+            continue
+        bits = [i for i in range(31, -1, -1) if (w >> i) & 1]      # highest first
+        for r in {0, len(bits) - 1, rng.randrange(len(bits))}:
+            want = 0
+            for i in bits[r:]:
+                want |= 1 << i
+            assert L.emu_drop_high_bits(w, r) == want, (hex(w), r)
+
+
+def _unit_want(words, base):
+    return np.array([base + 32 * k + i for k in range(128) for i in range(32) if (int(words[k]) >> i) & 1], dtype=np.uint32)
+
+
+def test_flatten_unit_every_density():
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        density = [0.0, 0.002, 0.01, 0.03, 0.08, 0.16, 0.1875, 0.3][trial % 8]
+        bits = rng.random((128, 32)) < density
+        if trial % 5 == 0:        # long stretches with no index at all (strings), also at both ends
+            lo, hi = sorted(int(v) for v in rng.integers(0, 129, 2))
+            bits[lo:hi] = False
+        if trial % 7 == 0:        # a few full words next to empty ones
+            for k in rng.integers(0, 128, 3):
+                bits[int(k)] = True
+        words = (bits * (1 << np.arange(32, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        want = _unit_want(words, 1000 * trial)
+        rc, got = emu.flatten_unit(words, value_base=1000 * trial)
+        if want.size > 768:
+            assert rc == 1
+        else:
+            assert rc == 0, (trial, rc)
+            assert np.array_equal(got, want), trial
+    # the smallest and the largest units the balanced path takes
+    for k, i in ((0, 0), (127, 31), (64, 5)):
+        words = np.zeros(128, dtype=np.uint32)
+        words[k] = 1 << i
+        rc, got = emu.flatten_unit(words)
+        assert rc == 0 and got.tolist() == [32 * k + i]
+    words = np.zeros(128, dtype=np.uint32)
+    words[:24] = 0xFFFFFFFF                                   # exactly 768 indexes in the first 24 words
+    rc, got = emu.flatten_unit(words)
+    assert rc == 0 and np.array_equal(got, np.arange(768, dtype=np.uint32))
